@@ -1,0 +1,54 @@
+// Shared helpers for the clb CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/clb.h"
+
+namespace clb {
+
+void set_error(const char* fmt, ...);
+int sm_count();
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#define CLB_CHECK_ARG(cond)                                                        \
+    do {                                                                           \
+        if (!(cond)) {                                                             \
+            clb::set_error("%s:%d: invalid argument: %s", __FILE__, __LINE__, #cond); \
+            return CLB_EINVAL;                                                     \
+        }                                                                          \
+    } while (0)
+
+#define CLB_CHECK_LAUNCH()                                                         \
+    do {                                                                           \
+        cudaError_t e__ = cudaGetLastError();                                      \
+        if (e__ != cudaSuccess) {                                                  \
+            clb::set_error("%s:%d: CUDA error: %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return CLB_ECUDA;                                                      \
+        }                                                                          \
+    } while (0)
+
+#define CLB_CUDA(call)                                                             \
+    do {                                                                           \
+        cudaError_t e__ = (call);                                                  \
+        if (e__ != cudaSuccess) {                                                  \
+            clb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return CLB_ECUDA;                                                      \
+        }                                                                          \
+    } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace clb

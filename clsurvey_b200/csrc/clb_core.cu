@@ -1,0 +1,49 @@
+// Error string, version, device queries.
+#include <stdarg.h>
+
+#include "clb_common.cuh"
+
+namespace clb {
+static thread_local char g_err[512] = "";
+static int g_mm_mode = CLB_MM_FP32_SIMT;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        else
+            return 148;  // B200
+    }
+    return cached;
+}
+int mm_mode() { return g_mm_mode; }
+}  // namespace clb
+
+extern "C" {
+const char* clb_last_error(void) { return clb::g_err; }
+int clb_version(void) { return 100; }
+int clb_sm_count(int* out) {
+    CLB_CHECK_ARG(out != nullptr);
+    int dev = 0, n = 0;
+    CLB_CUDA(cudaGetDevice(&dev));
+    CLB_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    *out = n;
+    return CLB_OK;
+}
+int clb_set_matmul_mode(int mode) {
+    CLB_CHECK_ARG(mode == CLB_MM_FP32_SIMT || mode == CLB_MM_TF32X3 || mode == CLB_MM_TF32X1);
+    clb::g_mm_mode = mode;
+    return CLB_OK;
+}
+int clb_get_matmul_mode(void) { return clb::g_mm_mode; }
+}

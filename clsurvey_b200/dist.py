@@ -1,0 +1,114 @@
+"""Data parallelism for the hot path.  The reference is single-process / single-GPU; this is new.
+
+One process per GPU (torchrun).  A training mini-batch of B samples is sharded by rows (rank r takes rows
+[r*B/W, (r+1)*B/W)); every rank computes d(mean-CE over the GLOBAL batch)/d(theta) on its shard (the loss head is
+given denom = B), so ONE sum-allreduce of the flat gradient buffer yields the exact global-batch gradient and all
+replicas then run the identical fused update.  Importance passes are sharded by WHOLE batches (the reference squares
+/ abs-es the batch-summed gradient, main_EWC.py:151-156, train_MAS.py:163-177) followed by one allreduce of omega.
+
+`torch.distributed` is the rendezvous plumbing; the data-path collective is ncclAllReduce on a communicator owned by
+libclb (clb_nccl_*), enqueued on the compute stream.  With the `gloo` backend (CPU tests) the collective falls back
+to torch.distributed.all_reduce on host tensors -- that path exists for host-logic tests only.
+"""
+import ctypes
+import os
+
+import torch
+
+from . import _capi
+
+_state = {"world": 1, "rank": 0, "comm": None, "backend": None}
+
+
+def world_size():
+    return _state["world"]
+
+
+def rank():
+    return _state["rank"]
+
+
+def is_distributed():
+    return _state["world"] > 1
+
+
+def init(backend=None):
+    """Initialise from torchrun's env (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*).  No-op for a single process."""
+    import torch.distributed as td
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return
+    rk = int(os.environ["RANK"])
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if torch.cuda.is_available():
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rk)))
+    if not td.is_initialized():
+        td.init_process_group(backend=backend, rank=rk, world_size=world)
+    _state.update(world=world, rank=rk, backend=backend)
+    if torch.cuda.is_available():
+        # own NCCL communicator behind the C ABI; the 128-byte unique id travels through torch.distributed
+        ident = (ctypes.c_char * 128)()
+        if rk == 0:
+            _capi.call("clb_nccl_unique_id", ctypes.addressof(ident))
+        box = [bytes(ident)]
+        td.broadcast_object_list(box, src=0)
+        ident = (ctypes.c_char * 128).from_buffer_copy(box[0])
+        comm = ctypes.c_void_p()
+        _capi.call("clb_nccl_init", ctypes.addressof(ident), rk, world, ctypes.addressof(comm))
+        _state["comm"] = comm
+
+
+def shutdown():
+    import torch.distributed as td
+    if _state["comm"] is not None:
+        _capi.call("clb_nccl_destroy", _state["comm"])
+        _state["comm"] = None
+    if td.is_available() and td.is_initialized():
+        td.destroy_process_group()
+    _state.update(world=1, rank=0, backend=None)
+
+
+def shard_rows(n, world=None, rk=None):
+    """Row range [lo, hi) of a mini-batch of n samples owned by this rank (equal shards; remainder to low ranks)."""
+    world = _state["world"] if world is None else world
+    rk = _state["rank"] if rk is None else rk
+    base, rem = divmod(n, world)
+    lo = rk * base + min(rk, rem)
+    return lo, lo + base + (1 if rk < rem else 0)
+
+
+def shard_batches(n_batches, world=None, rk=None):
+    """Indices of the importance-pass batches this rank processes (round robin: r, r+W, ...)."""
+    world = _state["world"] if world is None else world
+    rk = _state["rank"] if rk is None else rk
+    return list(range(rk, n_batches, world))
+
+
+def allreduce_flat(t):
+    """In-place sum-allreduce of a flat fp32 tensor on the current stream."""
+    if _state["world"] <= 1:
+        return
+    if t.is_cuda:
+        _capi.call("clb_nccl_allreduce_f32", _state["comm"], t.data_ptr(), t.numel(),
+                   torch.cuda.current_stream().cuda_stream)
+    else:
+        import torch.distributed as td
+        td.all_reduce(t)
+
+
+def allreduce_grads(engine):
+    if _state["world"] > 1:
+        allreduce_flat(engine.grad)
+        engine.n_launch += 1
+
+
+def allreduce_scalars(vals):
+    """Sum python numbers over ranks (epoch statistics: running loss / corrects)."""
+    if _state["world"] <= 1:
+        return list(vals)
+    import torch.distributed as td
+    dev = "cuda" if _state["backend"] == "nccl" else "cpu"
+    t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+    td.all_reduce(t)
+    return t.tolist()

@@ -1,0 +1,373 @@
+"""Engine: compiles a reference-style nn.Module (features / avgpool / classifier) into a static layer plan and runs
+forward, loss head and backward through the C ABI (include/clb.h) on flat fp32 buffers.
+
+PyTorch is used here for device memory, streams and (optionally) CUDA-graph capture only -- no torch op computes
+anything on the hot path.  Replaces `model(inputs)`, `criterion(outputs, labels)` and `loss.backward()` of the
+reference's train_model loops (src/methods/EWC/train_EWC.py:178-189 and twins) and of its importance passes
+(src/methods/EWC/main_EWC.py:138-157, src/methods/MAS/train_MAS.py:508-567).
+
+Layout in HBM:
+  theta, grad [, omega, theta_star, momentum, w]  : flat fp32 buffers, one slot per parameter tensor in
+      model.parameters() order, slot offsets rounded up to 4 elements (16 B) so every tensor is float4-aligned.
+      `p.data` / `p.grad` of the nn.Module are re-pointed at views of these buffers, so state_dict(), pickling and the
+      reference's `model.reg_params` dict keep working.
+  activations                                    : NCHW fp32, one buffer per layer output (kept for backward),
+      uint8 arg-max per max-pool, two ping-pong gradient buffers.
+"""
+import ctypes
+import weakref
+
+import torch
+import torch.nn as nn
+
+from . import _capi
+from ._capi import call
+
+LOSS_MEAN_CE, LOSS_SUM_NLL, LOSS_SUM_SQ = 0, 1, 2
+_ENGINES = weakref.WeakValueDictionary()   # id(parameter) -> Engine (lets the reference-style optimisers find it)
+
+
+def engine_of(params):
+    for p in params:
+        e = _ENGINES.get(id(p))
+        if e is not None:
+            return e
+    raise _capi.ClbError("parameters are not bound to a clsurvey_b200 Engine (call Engine(model, ...) first)")
+
+
+def get_engine(model, input_shape=None, max_batch=200, use_avgpool=True):
+    """Engine bound to `model` (created on first use; re-bound after a head swap / unpickling)."""
+    eng = getattr(model, "_clb_engine", None)
+    if eng is None:
+        if input_shape is None:
+            raise _capi.ClbError("get_engine: model has no engine yet, input_shape is required")
+        return Engine(model, input_shape, max_batch, use_avgpool=use_avgpool)
+    if (input_shape is not None and tuple(input_shape) != eng.input_shape) or max_batch > eng.max_batch:
+        return Engine(model, input_shape or eng.input_shape, max(max_batch, eng.max_batch), use_avgpool=use_avgpool)
+    eng.bind(model)
+    return eng
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Engine:
+    def __init__(self, model, input_shape=(3, 64, 64), max_batch=200, device="cuda", use_avgpool=True):
+        _capi.lib()                                   # fail loudly if the CUDA library is missing
+        if not torch.cuda.is_available():
+            raise _capi.ClbError("clsurvey_b200.Engine needs a CUDA device; there is no CPU fallback")
+        self.device = torch.device(device)
+        self.model = model
+        self.input_shape = tuple(input_shape)
+        self.max_batch = int(max_batch)
+        self.use_avgpool = use_avgpool
+        self.theta = self.grad = None
+        self.omega = self.theta_star = self.momentum = self.w = None
+        self.momentum_valid = False
+        self._grad_alt = None
+        self.bind(model)
+
+    # an Engine never travels with a pickled / deep-copied model (torch.save(model), copy.deepcopy(model))
+    def __reduce__(self):
+        return (type(None), ())
+
+    def __deepcopy__(self, memo):
+        return None
+
+    # ------------------------------------------------------------------ parameters <-> flat buffers
+    def bind(self, model=None):
+        """(Re)adopt the module's parameters into the flat buffers.  Call again after a head swap
+        (utils.replace_last_classifier_layer / main_EWC.py:49-53): values of the fresh head are copied in,
+        everything else (incl. omega/theta_star slots of unchanged tensors) keeps its place."""
+        model = self.model if model is None else model
+        self.model = model
+        params = list(model.parameters())
+        offs, off = [], 0
+        for p in params:
+            offs.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        total = off
+        same_layout = (self.theta is not None and total == self.theta.numel()
+                       and [tuple(p.shape) for p in params] == self.shapes)
+        old_theta = self.theta
+        if not same_layout:
+            self.theta = torch.zeros(total, dtype=torch.float32, device=self.device)
+            self.grad = torch.zeros(total, dtype=torch.float32, device=self.device)
+            self._grad_alt = None
+            self.omega = self.theta_star = self.momentum = self.w = None
+            self.momentum_valid = False
+        for k in [k for k, e in list(_ENGINES.items()) if e is self]:
+            del _ENGINES[k]
+        object.__setattr__(model, "_clb_engine", self)
+        self.params, self.offsets, self.numels = params, offs, [p.numel() for p in params]
+        self.shapes = [tuple(p.shape) for p in params]
+        self.total, self.n_real = total, sum(self.numels)
+        with torch.no_grad():
+            for p, o in zip(params, offs):
+                view = self.theta[o:o + p.numel()].view(p.shape)
+                if p.data.data_ptr() != view.data_ptr():
+                    view.copy_(p.data.to(self.device, torch.float32))
+                    p.data = view
+                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+                _ENGINES[id(p)] = self
+        del old_theta
+        self._compile()
+
+    def view(self, flat, i):
+        o = self.offsets[i]
+        return flat[o:o + self.numels[i]].view(self.shapes[i])
+
+    def ensure(self, name):
+        if getattr(self, name) is None:
+            setattr(self, name, torch.zeros(self.total, dtype=torch.float32, device=self.device))
+        return getattr(self, name)
+
+    # ------------------------------------------------------------------ plan
+    def _compile(self):
+        pidx = {id(p): i for i, p in enumerate(self.params)}
+        C, H, W = self.input_shape
+        ops = []
+
+        def add(**kw):
+            ops.append(kw)
+            return kw
+
+        feats = list(self.model.features.children())
+        i = 0
+        while i < len(feats):
+            m = feats[i]
+            if isinstance(m, nn.Conv2d):
+                assert m.groups == 1 and m.dilation == (1, 1) and m.stride[0] == m.stride[1] \
+                    and m.padding[0] == m.padding[1], "unsupported conv"
+                relu = i + 1 < len(feats) and isinstance(feats[i + 1], nn.ReLU)
+                R, S = m.kernel_size
+                P = (H + 2 * m.padding[0] - R) // m.stride[0] + 1
+                Q = (W + 2 * m.padding[0] - S) // m.stride[0] + 1
+                add(kind="conv", C=C, H=H, W=W, K=m.out_channels, R=R, S=S, stride=m.stride[0], pad=m.padding[0],
+                    relu=relu, w=pidx[id(m.weight)], b=pidx[id(m.bias)] if m.bias is not None else None,
+                    out_shape=(m.out_channels, P, Q))
+                C, H, W = m.out_channels, P, Q
+                i += 2 if relu else 1
+            elif isinstance(m, nn.MaxPool2d):
+                k = m.kernel_size if isinstance(m.kernel_size, int) else m.kernel_size[0]
+                s = m.stride if isinstance(m.stride, int) else m.stride[0]
+                assert (m.padding in (0, (0, 0))) and not m.ceil_mode, "unsupported pool"
+                PH, PW = (H - k) // s + 1, (W - k) // s + 1
+                add(kind="maxpool", C=C, H=H, W=W, k=k, stride=s, out_shape=(C, PH, PW))
+                H, W = PH, PW
+                i += 1
+            elif isinstance(m, nn.ReLU):
+                add(kind="relu", out_shape=(C, H, W))
+                i += 1
+            else:
+                raise NotImplementedError("features layer %r is outside the hot path" % (m,))
+        avg = getattr(self.model, "avgpool", None)
+        if self.use_avgpool and isinstance(avg, nn.AdaptiveAvgPool2d):
+            OH, OW = avg.output_size if isinstance(avg.output_size, tuple) else (avg.output_size,) * 2
+            add(kind="avgpool", C=C, H=H, W=W, OH=OH, OW=OW, out_shape=(C, OH, OW))
+            H, W = OH, OW
+        feat = C * H * W
+        cls = list(self.model.classifier.children())
+        i = 0
+        while i < len(cls):
+            m = cls[i]
+            if isinstance(m, nn.Linear):
+                assert m.in_features == feat, "classifier input %d != features output %d" % (m.in_features, feat)
+                relu = i + 1 < len(cls) and isinstance(cls[i + 1], nn.ReLU)
+                add(kind="linear", inf=feat, outf=m.out_features, relu=relu, w=pidx[id(m.weight)],
+                    b=pidx[id(m.bias)] if m.bias is not None else None, out_shape=(m.out_features,), cls_idx=i)
+                feat = m.out_features
+                i += 2 if relu else 1
+            elif isinstance(m, nn.Dropout):
+                add(kind="dropout", p=m.p, feat=feat, out_shape=(feat,), cls_idx=i, module=m)
+                i += 1
+            elif isinstance(m, nn.ReLU):
+                add(kind="relu", out_shape=(feat,))
+                i += 1
+            else:
+                raise NotImplementedError("classifier layer %r is outside the hot path" % (m,))
+        self.ops = ops
+        self.n_outputs = feat
+        B = self.max_batch
+        max_act = 1
+        for op in ops:
+            n = 1
+            for d in op["out_shape"]:
+                n *= d
+            op["out_numel"] = n
+            op["out"] = torch.empty(B * n, dtype=torch.float32, device=self.device)
+            max_act = max(max_act, n)
+            if op["kind"] == "maxpool":
+                op["argmax"] = torch.empty(B * n, dtype=torch.uint8, device=self.device)
+        in_numel = self.input_shape[0] * self.input_shape[1] * self.input_shape[2]
+        max_act = max(max_act, in_numel)
+        self.dbuf = [torch.empty(B * max_act, dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.dlogits = torch.empty(B * self.n_outputs, dtype=torch.float32, device=self.device)
+        ws_bytes, wt_elems = 16, 4
+        for op in ops:
+            if op["kind"] == "conv":
+                ws_bytes = max(ws_bytes, _capi.lib().clb_conv2d_wgrad_ws(B, op["C"], op["H"], op["W"], op["K"], op["R"],
+                                                                          op["S"], op["stride"], op["pad"]))
+                wt_elems = max(wt_elems, op["K"] * op["C"] * op["R"] * op["S"])
+        self.ws = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=self.device)
+        self.wt_ws = torch.empty(wt_elems, dtype=torch.float32, device=self.device)
+        self.loss_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.correct_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.n_launch = 0
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x, train=False, masks=None):
+        """x: [n, C, H, W] fp32 CUDA contiguous.  Returns logits [n, n_outputs] (a view of an internal buffer).
+        masks: {classifier child index: pre-scaled mask tensor [n, feat] or [feat]} for active Dropout layers."""
+        n = x.shape[0]
+        assert n <= self.max_batch and x.is_cuda and x.dtype == torch.float32
+        x = x.contiguous()
+        assert tuple(x.shape[1:]) == self.input_shape, (x.shape, self.input_shape)
+        s = _stream()
+        cur = x
+        self._n = n
+        self._train = train
+        self._masks = {}
+        for op in self.ops:
+            op["inp"] = cur
+            k = op["kind"]
+            if k == "conv":
+                call("clb_conv2d_fwd", _ptr(cur), _ptr(self.view(self.theta, op["w"])),
+                     _ptr(self.view(self.theta, op["b"])) if op["b"] is not None else 0, _ptr(op["out"]), n, op["C"],
+                     op["H"], op["W"], op["K"], op["R"], op["S"], op["stride"], op["pad"], int(op["relu"]), s)
+                cur = op["out"]
+            elif k == "maxpool":
+                call("clb_maxpool_fwd", _ptr(cur), _ptr(op["out"]), _ptr(op["argmax"]), n, op["C"], op["H"], op["W"],
+                     op["k"], op["stride"], s)
+                cur = op["out"]
+            elif k == "avgpool":
+                call("clb_adaptive_avgpool_fwd", _ptr(cur), _ptr(op["out"]), n, op["C"], op["H"], op["W"], op["OH"],
+                     op["OW"], s)
+                cur = op["out"]
+            elif k == "linear":
+                call("clb_linear_fwd", _ptr(cur), _ptr(self.view(self.theta, op["w"])),
+                     _ptr(self.view(self.theta, op["b"])) if op["b"] is not None else 0, _ptr(op["out"]), n, op["inf"],
+                     op["outf"], int(op["relu"]), s)
+                cur = op["out"]
+            elif k == "dropout":
+                if not train:
+                    continue
+                mask = None if masks is None else masks.get(op["cls_idx"])
+                if mask is None:
+                    mask = self.draw_dropout_mask(op, n)
+                mask = mask.to(self.device, torch.float32).contiguous()
+                self._masks[op["cls_idx"]] = mask
+                rows = 1 if mask.dim() == 1 else mask.shape[0]
+                call("clb_mask_mul", _ptr(cur), _ptr(mask), _ptr(op["out"]), n, op["feat"], rows, s)
+                cur = op["out"]
+            elif k == "relu":
+                raise NotImplementedError("stand-alone ReLU (not following Conv2d/Linear)")
+            self.n_launch += 1
+        self.logits = cur[:n * self.n_outputs].view(n, self.n_outputs)
+        return self.logits
+
+    def draw_dropout_mask(self, op, n):
+        """Element mask from the HOST torch generator: F.dropout(x, p) == x * bernoulli(1-p)/(1-p) under the same seed
+        (SURVEY.md hard part 4) -- the engine receives masks, it does not regenerate them."""
+        keep = 1.0 - op["p"]
+        return torch.empty(n, op["feat"]).bernoulli_(keep).div_(keep)
+
+    # ------------------------------------------------------------------ loss head
+    def loss_head(self, labels, mode=LOSS_MEAN_CE, denom=None, col_off=0, ncols=None, want_grad=True):
+        """Fused softmax / loss / #correct / dlogits on the last forward's logits.  Device scalars only (no sync)."""
+        n = self._n
+        ncols = self.n_outputs - col_off if ncols is None else ncols
+        denom = float(n if denom is None else denom)
+        self.loss_dev.zero_()
+        self.correct_dev.zero_()
+        if labels is not None:
+            labels = labels.to(self.device, torch.int64).contiguous()
+        self._labels = labels
+        call("clb_softmax_loss", _ptr(self.logits), self.n_outputs, col_off, ncols, _ptr(labels), n, mode, denom,
+             _ptr(self.loss_dev), _ptr(self.correct_dev), _ptr(self.dlogits) if want_grad else 0, _stream())
+        self.n_launch += 1
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, accumulate=False):
+        """dlogits -> parameter gradients (flat self.grad).  accumulate=True adds to the existing gradient
+        (GEM memory mini-batches, gem.py:239-256, never zero the grads in between)."""
+        n, s = self._n, _stream()
+        gdst = self.grad
+        if accumulate:
+            if self._grad_alt is None:
+                self._grad_alt = torch.zeros_like(self.grad)
+            gdst = self._grad_alt
+        d, other = self.dlogits, 0
+        first_param_op = next(i for i, op in enumerate(self.ops) if op["kind"] in ("conv", "linear"))
+        relu_done = set()
+        for i in range(len(self.ops) - 1, -1, -1):
+            op = self.ops[i]
+            k = op["kind"]
+            if k == "linear":
+                if op["relu"]:
+                    call("clb_relu_bwd", _ptr(d), _ptr(op["out"]), _ptr(d), n * op["outf"], s)
+                call("clb_linear_wgrad", _ptr(op["inp"]), _ptr(d), _ptr(self.view(gdst, op["w"])),
+                     _ptr(self.view(gdst, op["b"])) if op["b"] is not None else 0, n, op["inf"], op["outf"], s)
+                if i != first_param_op:
+                    nxt = self.dbuf[other]
+                    call("clb_linear_dgrad", _ptr(d), _ptr(self.view(self.theta, op["w"])), _ptr(nxt), n, op["inf"],
+                         op["outf"], s)
+                    d, other = nxt, other ^ 1
+                self.n_launch += 3
+            elif k == "dropout":
+                if self._train and op["cls_idx"] in self._masks:
+                    mask = self._masks[op["cls_idx"]]
+                    rows = 1 if mask.dim() == 1 else mask.shape[0]
+                    call("clb_mask_mul", _ptr(d), _ptr(mask), _ptr(d), n, op["feat"], rows, s)
+            elif k == "avgpool":
+                nxt = self.dbuf[other]
+                call("clb_adaptive_avgpool_bwd", _ptr(d), _ptr(nxt), n, op["C"], op["H"], op["W"], op["OH"], op["OW"], s)
+                d, other = nxt, other ^ 1
+            elif k == "maxpool":
+                prev = self.ops[i - 1] if i > 0 else None
+                fuse = prev is not None and prev["kind"] == "conv" and prev["relu"]
+                nxt = self.dbuf[other]
+                call("clb_maxpool_bwd", _ptr(d), _ptr(op["argmax"]), _ptr(prev["out"]) if fuse else 0, _ptr(nxt), n,
+                     op["C"], op["H"], op["W"], op["k"], op["stride"], s)
+                if fuse:
+                    relu_done.add(i - 1)
+                d, other = nxt, other ^ 1
+                self.n_launch += 1
+            elif k == "conv":
+                if op["relu"] and i not in relu_done:
+                    call("clb_relu_bwd", _ptr(d), _ptr(op["out"]), _ptr(d), n * op["out_numel"], s)
+                call("clb_conv2d_wgrad", _ptr(op["inp"]), _ptr(d), _ptr(self.view(gdst, op["w"])),
+                     _ptr(self.view(gdst, op["b"])) if op["b"] is not None else 0, _ptr(self.ws), self.ws.numel() * 4,
+                     n, op["C"], op["H"], op["W"], op["K"], op["R"], op["S"], op["stride"], op["pad"], s)
+                if i != first_param_op:
+                    nxt = self.dbuf[other]
+                    call("clb_conv2d_dgrad", _ptr(d), _ptr(self.view(self.theta, op["w"])), _ptr(nxt),
+                         _ptr(self.wt_ws), n, op["C"], op["H"], op["W"], op["K"], op["R"], op["S"], op["stride"],
+                         op["pad"], s)
+                    d, other = nxt, other ^ 1
+                self.n_launch += 4
+        if accumulate:
+            call("clb_axpby", _ptr(self.grad), _ptr(self.grad), _ptr(gdst), 1.0, self.total, s)
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    # ------------------------------------------------------------------ composite steps
+    def fwd_loss_bwd(self, x, y, mode=LOSS_MEAN_CE, denom=None, train=True, masks=None, col_off=0, ncols=None,
+                     accumulate=False):
+        self.forward(x, train=train, masks=masks)
+        self.loss_head(y, mode, denom, col_off, ncols, want_grad=True)
+        self.backward(accumulate=accumulate)
+
+    def fwd_loss(self, x, y, mode=LOSS_MEAN_CE, col_off=0, ncols=None):
+        self.forward(x, train=False)
+        self.loss_head(y, mode, None, col_off, ncols, want_grad=False)
+
+    def read_loss_correct(self):
+        """One device->host read of (loss, #correct) -- the reference does this every batch (train_EWC.py:196-197)."""
+        return float(self.loss_dev.item()), int(self.correct_dev.item())

@@ -1,0 +1,160 @@
+/*
+ * clb.h -- C ABI of the B200-native continual-learning hot-path engine ("clb").
+ *
+ * This is the drop-in boundary of the repo.  The reference (Mattdl/CLsurvey) is
+ * pure Python on PyTorch and has no FFI: its operator-level boundary is torch itself
+ * (`model(inputs)`, `criterion(outputs, labels)`, `loss.backward()`, `optimizer.step(reg_params)`,
+ * src/methods/EWC/train_EWC.py:178-189).  Each entry point below replaces one group of those
+ * implicit ATen/cuDNN/cuBLAS calls; the reference call site it replaces is cited per function.
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 = CLB_E* on failure; clb_last_error() gives the text
+ *   - all tensor pointers are caller-owned DEVICE pointers, fp32 contiguous (labels int64, argmax u8)
+ *   - activations NCHW, conv weights [K,C,R,S], linear weights [out,in]  (the reference's layouts)
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous and stream-ordered,
+ *     allocation-free and CUDA-graph capturable (workspaces are passed in by the caller)
+ *   - one host thread per handle/rank; no global mutable state besides the last-error string
+ */
+#ifndef CLB_H_
+#define CLB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLB_OK 0
+#define CLB_EINVAL (-1)   /* bad argument / unsupported shape */
+#define CLB_ECUDA (-2)    /* CUDA runtime error (text in clb_last_error) */
+#define CLB_EWORKSPACE (-3) /* workspace too small */
+#define CLB_ENCCL (-4)    /* NCCL error / library not loadable */
+
+/* loss modes of clb_softmax_loss */
+#define CLB_LOSS_MEAN_CE 0 /* nn.CrossEntropyLoss()                       main_EWC.py:55 */
+#define CLB_LOSS_SUM_NLL 1 /* nll_loss(log_softmax, size_average=False)   main_EWC.py:148 */
+#define CLB_LOSS_SUM_SQ 2  /* MSELoss(size_average=False) vs zeros         train_MAS.py:552-560 */
+
+/* GEMM precision modes (clb_set_matmul_mode) */
+#define CLB_MM_FP32_SIMT 0 /* exact fp32 FFMA path */
+#define CLB_MM_TF32X3 1    /* tcgen05 kind::tf32, 3-pass split (hi*hi + hi*lo + lo*hi), fp32 accum in TMEM */
+#define CLB_MM_TF32X1 2    /* tcgen05 kind::tf32 single pass (fast, NOT parity mode) */
+
+const char* clb_last_error(void);
+int clb_version(void);
+int clb_sm_count(int* out);
+int clb_set_matmul_mode(int mode);
+int clb_get_matmul_mode(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Layer kernels (a2, a3).  Replace model(inputs) / loss.backward() of train_EWC.py:181-187.
+ * ---------------------------------------------------------------------------------------- */
+
+/* y = conv2d(x, w) + bias, optional fused ReLU.  nn.Conv2d + nn.ReLU  (models/VGGSlim.py:34-38) */
+int clb_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int N, int C, int H, int W, int K,
+                   int R, int S, int stride, int pad, int relu, void* stream);
+/* dx = conv2d_backward_input(dy, w).  wt_ws: scratch of K*C*R*S floats (transposed/flipped weights). */
+int clb_conv2d_dgrad(const float* dy, const float* w, float* dx, float* wt_ws, int N, int C, int H, int W, int K,
+                     int R, int S, int stride, int pad, void* stream);
+/* dw = conv2d_backward_weight(x, dy), dbias = sum dy.  ws: split-K partials, ws_bytes >= clb_conv2d_wgrad_ws(...) */
+size_t clb_conv2d_wgrad_ws(int N, int C, int H, int W, int K, int R, int S, int stride, int pad);
+int clb_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias, float* ws, size_t ws_bytes, int N,
+                     int C, int H, int W, int K, int R, int S, int stride, int pad, void* stream);
+
+/* y[M,out] = x[M,in] @ w[out,in]^T + bias, optional ReLU.  nn.Linear (+ReLU)  (VGGSlim.py:58-73) */
+int clb_linear_fwd(const float* x, const float* w, const float* bias, float* y, int M, int in, int out, int relu,
+                   void* stream);
+int clb_linear_dgrad(const float* dy, const float* w, float* dx, int M, int in, int out, void* stream);
+int clb_linear_wgrad(const float* x, const float* dy, float* dw, float* dbias, int M, int in, int out, void* stream);
+
+/* dx = dy * (y > 0)   (ReLU backward from the saved OUTPUT; in place allowed: dx == dy) */
+int clb_relu_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream);
+
+/* MaxPool2d(k, stride) fwd (argmax saved as window-local index, first max wins like ATen) / bwd (gather, no atomics).
+ * bwd optionally fuses the ReLU mask of the layer in front: dx *= (x_relu_out > 0) when x_relu_out != NULL. */
+int clb_maxpool_fwd(const float* x, float* y, uint8_t* argmax, int N, int C, int H, int W, int k, int stride,
+                    void* stream);
+int clb_maxpool_bwd(const float* dy, const uint8_t* argmax, const float* x_relu_out, float* dx, int N, int C, int H,
+                    int W, int k, int stride, void* stream);
+
+/* AdaptiveAvgPool2d((OH,OW))  (torchvision AlexNet.avgpool) */
+int clb_adaptive_avgpool_fwd(const float* x, float* y, int N, int C, int H, int W, int OH, int OW, void* stream);
+int clb_adaptive_avgpool_bwd(const float* dy, float* dx, int N, int C, int H, int W, int OH, int OW, void* stream);
+
+/* y[r, c] = x[r, c] * mask[(mask_rows == 1 ? 0 : r), c]   dropout with a host-drawn, pre-scaled mask
+ * (F.dropout element mask: mask_rows == rows; GEM per-unit mask shared over the batch, gem.py:183-192: mask_rows == 1) */
+int clb_mask_mul(const float* x, const float* mask, float* y, int rows, int cols, int mask_rows, void* stream);
+
+/* Loss head on logits[B, ld] restricted to columns [col_off, col_off+ncols)  (GEM head masking, gem.py:199-203,242).
+ * mode: CLB_LOSS_*.  dlogits (B x ld, may be NULL) receives d loss / d logits * grad_scale (zeros outside the slice).
+ * loss_out[0] += loss contribution (caller zeroes), correct_out[0] += #argmax==label.
+ * For MEAN_CE the mean is over `mean_denominator` rows (global batch under data parallelism). */
+int clb_softmax_loss(const float* logits, int ld, int col_off, int ncols, const int64_t* labels, int B, int mode,
+                     float mean_denominator, float* loss_out, int* correct_out, float* dlogits, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimiser / importance streaming kernels (a4-a11).  One launch over the flat parameter buffer.
+ * ---------------------------------------------------------------------------------------- */
+
+/* Weight_Regularized_SGD.step (EWC/train_EWC.py:46-84, MAS/train_MAS.py:45-93) and plain optim.SGD (main_SGD.py:74):
+ *   d = g*grad_scale [+ (theta-theta*) * (omega * two_lambda) for i < n_penalised] [+ wd*theta]
+ *   buf = first_step ? d : mu*buf + d ;  theta -= lr*buf
+ * omega/theta_star may be NULL when n_penalised == 0. */
+int clb_sgd_penalty_step(float* theta, const float* g, const float* omega, const float* theta_star, float* buf,
+                         int64_t n, int64_t n_penalised, float two_lambda, float lr, float momentum,
+                         float weight_decay, float grad_scale, int first_step, void* stream);
+
+/* Elastic_SGD.step (SI/train_SI.py:48-125): as above for ALL n elements plus  w += -(theta_new - theta_old) * g0 */
+int clb_si_step(float* theta, const float* g, const float* omega, const float* theta_star, float* buf, float* w,
+                int64_t n, float two_lambda, float lr, float momentum, float weight_decay, float grad_scale,
+                int first_step, void* stream);
+
+/* diag_fisher accumulate (EWC/main_EWC.py:151-156):  omega += g*g / data_len */
+int clb_fisher_accum(float* omega, const float* g, float data_len, int64_t n, void* stream);
+
+/* Objective_After_SGD.step (MAS/train_MAS.py:163-177):  omega = (omega*prev_size + |g|) / curr_size */
+int clb_mas_accum(float* omega, const float* g, float prev_size, float curr_size, int64_t n, void* stream);
+
+/* update_reg_params (SI/train_SI.py:390-417):  omega += max(w / ((theta-theta*)^2 + slack), 0); w = 0; theta* = theta */
+int clb_si_consolidate(float* omega, float* w, const float* theta, float* theta_star, float slack, int64_t n,
+                       void* stream);
+
+/* accumelate_reg_params (EWC/main_EWC.py:205-232):  dst = a + b*scale_b   (also used to finish a sharded pass) */
+int clb_axpby(float* dst, const float* a, const float* b, float scale_b, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GEM (a15, a16).  Gradient memory is TASK-MAJOR G[n_tasks][ld] (reference: [P, n_tasks], gem.py:131-132).
+ * ---------------------------------------------------------------------------------------- */
+
+/* dots[i] = <g, G[idx[i]]>, gram[i][j] = <G[idx[i]], G[idx[j]]>  (fp64 accumulation of exact fp32 products);
+ * replaces torch.mm(grads[:,t], grads.index_select(1,indx)) (gem.py:275-276) and the host MM^T of gem.py:73.
+ * dots/gram must be zeroed by the caller (they are accumulated with one atomic per CTA). k <= 16. */
+int clb_gem_dots_gram(const float* g, const float* G, int64_t ld, int64_t P, const int* idx_dev, int k, double* dots,
+                      double* gram, void* stream);
+
+/* Device QP of project2cone2 (gem.py:73-78): P = 0.5(gram+gram^T)+eps I, q = -dots, min 1/2 v'Pv + dots'v s.t. v >= margin.
+ * Writes v[k] and viol[0] = #(dots < 0).  If viol == 0, v is set to 0 (no projection). */
+int clb_gem_solve_qp(const double* dots, const double* gram, int k, double margin, double eps, double* v, int* viol,
+                     void* stream);
+/* same solver on the host (tests / INTEGRATION.md); pointers are HOST pointers */
+int clb_gem_solve_qp_host(const double* dots, const double* gram, int k, double margin, double eps, double* v,
+                          int* viol);
+
+/* g[i] = float( sum_j v[j]*G[idx[j]][i] + g[i] )  computed in fp64 when viol[0] != 0 (gem.py:79-80) */
+int clb_gem_project(float* g, const float* G, int64_t ld, int64_t P, const int* idx_dev, int k, const double* v,
+                    const int* viol, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Data parallel (8e): thin wrapper over ncclAllReduce(sum, fp32) on a communicator created here.
+ * ---------------------------------------------------------------------------------------- */
+int clb_nccl_unique_id(void* out128);                              /* rank 0: 128-byte ncclUniqueId */
+int clb_nccl_init(const void* id128, int rank, int world, void** comm_out);
+int clb_nccl_allreduce_f32(void* comm, float* buf, int64_t n, void* stream);
+int clb_nccl_destroy(void* comm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLB_H_ */

@@ -1,0 +1,273 @@
+"""Generate tests/golden/*.pt by RUNNING THE UNMODIFIED REFERENCE on CPU (TEST INFRASTRUCTURE ONLY).
+
+    python -m oracle.gen_golden            # needs /root/reference (authoring container only)
+
+The reference ships no tests / golden vectors, so the fixtures are made here
+from the reference's own functions, imported through oracle/refshim.py:
+
+  finetune : methods.Finetune.train_SGD.train_model                       (a1)
+  ewc      : methods.EWC.main_EWC.accumulate_EWC_weights (diag_fisher) +
+             methods.EWC.train_EWC.{Weight_Regularized_SGD, train_model}   (a4-a7)
+  mas      : methods.MAS.main_MAS.accumulate_objective_based_weights +
+             methods.MAS.train_MAS.{Weight_Regularized_SGD, train_model}   (a6, a8, a9)
+  si       : methods.SI.train_SI.{initialize_reg_params, Elastic_SGD, train_model,
+             update_reg_params}                                            (a10-a12)
+  gem      : methods.rehearsal.model.gem.Net.observe                       (a13-a16)
+  qp       : known-answer vectors for project2cone2's QP (oracle/qp.py, cross-checked with scipy)
+
+Inputs are synthetic (torch.Generator seeds recorded in each fixture), the seed protocol is the
+reference's utils.set_random(7).  The model is a reference VGGSlim with a small extra config
+entry ('tiny': 3 conv stages) so that fixtures stay < 1 MB; the code path is identical to
+small_VGG9 / 11normal.
+"""
+import contextlib
+import copy
+import io
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import refshim  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+TINY_CFG = [8, "M", 16, "M", 16, 16, "M"]
+IN_HW, NCLS, NTRAIN, NVAL, BS = 16, 5, 64, 32, 16
+
+
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def make_task(seed, n):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, 3, IN_HW, IN_HW, generator=g)
+    y = torch.randint(0, NCLS, (n,), generator=g)
+    return x, y
+
+
+def loaders_for(task_seed):
+    xt, yt = make_task(task_seed, NTRAIN)
+    xv, yv = make_task(task_seed + 1000, NVAL)
+    mk = lambda x, y: torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=BS, shuffle=False)
+    return {"train": mk(xt, yt), "val": mk(xv, yv)}, {"train": NTRAIN, "val": NVAL}, (xt, yt, xv, yv)
+
+
+class RecCE(nn.Module):
+    """criterion wrapper that records every batch loss (the criterion is an argument of train_model)."""
+
+    def __init__(self):
+        super().__init__()
+        self.ce = nn.CrossEntropyLoss()
+        self.losses = []
+
+    def forward(self, out, y):
+        l = self.ce(out, y)
+        self.losses.append(float(l.item()))
+        return l
+
+
+def new_model(dropout=False):
+    import models.VGGSlim as V
+    import utilities.utils as U
+    V.cfg["tiny"] = TINY_CFG
+    U.set_random(7)
+    return V.VGGSlim(config="tiny", num_classes=NCLS, classifier_inputdim=16 * 2 * 2,
+                     classifier_dim1=32, classifier_dim2=32, dropout=dropout)
+
+
+def sd(model):
+    return {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+
+def reg_dump(model, keys=("omega", "init_val", "w")):
+    out = {}
+    for n, p in model.named_parameters():
+        if p in model.reg_params:
+            out[n] = {k: model.reg_params[p][k].detach().clone() for k in keys if k in model.reg_params[p]}
+    return out
+
+
+def save_dsets(path, x, y):
+    ds = torch.utils.data.TensorDataset(x, y)
+    ds.classes = list(range(NCLS))
+    torch.save({"train": ds, "val": ds}, path)
+
+
+def gen_finetune(tmp):
+    import torch.optim as optim
+    import methods.Finetune.train_SGD as T
+    out = {}
+    for tag, wd in (("wd0", 0.0), ("wd5e-4", 5e-4)):
+        model = new_model()
+        init = sd(model)
+        loaders, sizes, data = loaders_for(11)
+        crit = RecCE()
+        opt = optim.SGD(model.parameters(), 0.05, momentum=0.9, weight_decay=wd)
+        with quiet():
+            model, best = T.train_model(model, crit, opt, 0.05, loaders, sizes, False, 3, exp_dir=tmp, resume="",
+                                        save_models_mode=False)
+        out[tag] = dict(init=init, final=sd(model), best_acc=float(best), losses=crit.losses, lr=0.05, wd=wd,
+                        epochs=3, data=data)
+    torch.save(out, os.path.join(GOLDEN, "finetune.pt"))
+
+
+def _penalty_method(tmp, which):
+    """EWC / MAS: importance pass on task A data, new head, penalised training on task B; then repeat (accumulate)."""
+    if which == "ewc":
+        import methods.EWC.main_EWC as M
+        import methods.EWC.train_EWC as T
+        accumulate = lambda model, path: M.accumulate_EWC_weights(None, [path], model, BS)
+    else:
+        import methods.MAS.main_MAS as M
+        import methods.MAS.train_MAS as T
+        accumulate = lambda model, path: M.accumulate_objective_based_weights(None, [path], model, BS, "L2",
+                                                                               test_set="train")
+    model = new_model()
+    out = dict(init=sd(model), rounds=[])
+    lam = 50.0 if which == "ewc" else 3.0
+    for rnd, (seed_prev, seed_cur) in enumerate(((21, 22), (22, 23))):
+        xp, yp = make_task(seed_prev, NTRAIN)
+        dpath = os.path.join(tmp, "%s_prev_%d.pth" % (which, rnd))
+        save_dsets(dpath, xp, yp)
+        with quiet():
+            model = accumulate(model, dpath)
+        model.reg_params["lambda"] = lam
+        omega_after_pass = reg_dump(model, ("omega", "init_val"))
+        torch.manual_seed(100 + rnd)                       # fresh-head init drawn from the host generator
+        model.classifier._modules["4"] = nn.Linear(32, NCLS)
+        head = {k: v.clone() for k, v in model.classifier._modules["4"].state_dict().items()}
+        loaders, sizes, data = loaders_for(seed_cur)
+        crit = RecCE()
+        opt = T.Weight_Regularized_SGD(model.parameters(), 0.05, momentum=0.9, weight_decay=1e-4 if rnd else 0.0)
+        with quiet():
+            model, best = T.train_model(model, crit, opt, 0.05, loaders, sizes, False, 2, exp_dir=tmp + "/", resume="")
+        out["rounds"].append(dict(prev_data=(xp, yp), data=data, lam=lam, lr=0.05, wd=1e-4 if rnd else 0.0, epochs=2,
+                                  reg_after_pass=omega_after_pass, new_head=head, final=sd(model),
+                                  best_acc=float(best), losses=crit.losses))
+    torch.save(out, os.path.join(GOLDEN, which + ".pt"))
+
+
+def gen_si(tmp):
+    import methods.SI.train_SI as T
+    model = new_model()
+    out = dict(init=sd(model), rounds=[])
+    lam = 2.0
+    for rnd, seed in enumerate((31, 32)):
+        if rnd == 0:
+            with quiet():
+                reg = T.initialize_reg_params(model)
+        else:
+            torch.manual_seed(200 + rnd)
+            model.classifier._modules["4"] = nn.Linear(32, NCLS)
+            params = list(model.parameters())
+            model.reg_params.pop(params[-1], None)
+            model.reg_params.pop(params[-2], None)
+            with quiet():
+                reg = T.update_reg_params(model)
+        reg["lambda"] = lam
+        model.reg_params = reg
+        head = {k: v.clone() for k, v in model.classifier._modules["4"].state_dict().items()}
+        reg_before = reg_dump(model)
+        loaders, sizes, data = loaders_for(seed)
+        crit = RecCE()
+        opt = T.Elastic_SGD(model.parameters(), 0.05, momentum=0.9, weight_decay=0.0)
+        with quiet():
+            model, best = T.train_model(model, crit, opt, 0.05, loaders, sizes, False, 2, exp_dir=tmp + "/", resume="")
+        out["rounds"].append(dict(data=data, lam=lam, lr=0.05, epochs=2, head=head, reg_before=reg_before,
+                                  reg_after=reg_dump(model), final=sd(model), best_acc=float(best),
+                                  losses=crit.losses))
+    torch.save(out, os.path.join(GOLDEN, "si.pt"))
+
+
+def gen_gem(tmp):
+    refshim.patch_gem_memory()
+    import methods.rehearsal.model.gem as G
+    n_tasks, n_mem, bs = 3, 24, 16
+    base = new_model(dropout=True)
+    init = sd(base)
+    mpath = os.path.join(tmp, "gem_prev.pth")
+    torch.save(base, mpath)
+    args = types.SimpleNamespace(prev_model_path=mpath, cuda=False, n_memories=n_mem, lr=0.05, weight_decay=0.0,
+                                 memory_strength=0.5, batch_size=bs, nc_per_task=[NCLS] * n_tasks,
+                                 task_imgfolders={"train": types.SimpleNamespace(transform=None)})
+    with quiet():
+        net = G.Net(0, NCLS * n_tasks, n_tasks, args)
+    wrapped_init = sd(net.net)
+    steps = []
+    store = refshim.KeyedTensorStore.store
+    store.clear()
+    datas = []
+    torch.manual_seed(77)                                   # dropout unit masks come from the host generator
+    for t in range(n_tasks):
+        x, y = make_task(41 + t, 48)
+        datas.append((x, y))
+        for b in range(3):
+            xb, yb = x[b * bs:(b + 1) * bs], y[b * bs:(b + 1) * bs]
+            keys = [t * 1000 + b * bs + i for i in range(bs)]
+            for k, xi in zip(keys, xb):
+                store[k] = xi
+            rng_state = torch.get_rng_state()
+            with quiet():
+                loss, corr, stats = net.observe(xb, t, yb, keys, args)
+            steps.append(dict(t=t, keys=keys, loss=float(loss.item()), correct=int(corr.item()),
+                              violations=int(stats["projected_grads"][0]), mem_cnt=net.mem_cnt,
+                              masks={k: v.clone() for k, v in net.dropout_masks.items()},
+                              rng_state=rng_state,
+                              grad_col=net.grads[:, t].clone(),
+                              params=torch.cat([p.data.reshape(-1) for p in net.parameters()]).clone()))
+    out = dict(init=init, wrapped_init=wrapped_init, data=datas, steps=steps, n_tasks=n_tasks, n_mem=n_mem, bs=bs,
+               lr=0.05, margin=0.5, memory_labels=net.memory_labels.clone(),
+               exemplars={t: list(net.memory_data[t]) for t in range(n_tasks)} if net.memory_data is not None else {},
+               grads=net.grads.clone(), final=sd(net.net))
+    torch.save(out, os.path.join(GOLDEN, "gem.pt"))
+
+
+def gen_qp():
+    import scipy.optimize as so
+    from oracle import qp
+    rng = np.random.default_rng(7)
+    cases = []
+    for trial in range(24):
+        k = int(rng.integers(1, 10))
+        M = rng.standard_normal((k, 64))
+        M[:, :4] *= 4.0
+        if trial % 4 == 0 and k > 1:
+            M[1] = 0.9 * M[0] + 0.1 * M[1]                  # strongly correlated memories
+        g = rng.standard_normal(64)
+        margin = [0.0, 0.5, 1.0][trial % 3]
+        P = M @ M.T
+        P = 0.5 * (P + P.T) + 1e-3 * np.eye(k)
+        q = -(M @ g)
+        v = qp.solve_lower_bounded_qp(P, q, np.full(k, margin))
+        f = lambda z: 0.5 * z @ P @ z - q @ z
+        r = so.minimize(f, np.full(k, margin + 1.0), jac=lambda z: P @ z - q, bounds=[(margin, None)] * k,
+                        method="L-BFGS-B", options=dict(ftol=1e-15, gtol=1e-12, maxiter=20000))
+        assert np.abs(r.x - v).max() <= 1e-6 * max(1.0, np.abs(v).max()), (trial, r.x, v)
+        cases.append(dict(M=torch.from_numpy(M), g=torch.from_numpy(g), margin=margin, v=torch.from_numpy(v)))
+    torch.save(cases, os.path.join(GOLDEN, "qp.pt"))
+
+
+def main():
+    refshim.install()
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.set_num_threads(1)                                # fixed reduction order for the fixtures
+    with tempfile.TemporaryDirectory() as tmp:
+        gen_finetune(tmp)
+        _penalty_method(tmp, "ewc")
+        _penalty_method(tmp, "mas")
+        gen_si(tmp)
+        gen_gem(tmp)
+    gen_qp()
+    for f in sorted(os.listdir(GOLDEN)):
+        print(f, os.path.getsize(os.path.join(GOLDEN, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -70,7 +70,18 @@ class Engine:
         self.omega = self.theta_star = self.momentum = self.w = None
         self.momentum_valid = False
         self._grad_alt = None
+        self.conv_events = None       # bench.py: list of (start, end) CUDA events around every conv launch
         self.bind(model)
+
+    def _timed(self, fn, *a):
+        """Run one C-ABI call; when bench.py asked for it, bracket it with CUDA events on the launching stream."""
+        if self.conv_events is None:
+            return fn(*a)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn(*a)
+        e1.record()
+        self.conv_events.append((e0, e1))
 
     # an Engine never travels with a pickled / deep-copied model (torch.save(model), copy.deepcopy(model))
     def __reduce__(self):
@@ -237,7 +248,7 @@ class Engine:
             op["inp"] = cur
             k = op["kind"]
             if k == "conv":
-                call("clb_conv2d_fwd", _ptr(cur), _ptr(self.view(self.theta, op["w"])),
+                self._timed(call, "clb_conv2d_fwd", _ptr(cur), _ptr(self.view(self.theta, op["w"])),
                      _ptr(self.view(self.theta, op["b"])) if op["b"] is not None else 0, _ptr(op["out"]), n, op["C"],
                      op["H"], op["W"], op["K"], op["R"], op["S"], op["stride"], op["pad"], int(op["relu"]), s)
                 cur = op["out"]
@@ -341,12 +352,12 @@ class Engine:
             elif k == "conv":
                 if op["relu"] and i not in relu_done:
                     call("clb_relu_bwd", _ptr(d), _ptr(op["out"]), _ptr(d), n * op["out_numel"], s)
-                call("clb_conv2d_wgrad", _ptr(op["inp"]), _ptr(d), _ptr(self.view(gdst, op["w"])),
+                self._timed(call, "clb_conv2d_wgrad", _ptr(op["inp"]), _ptr(d), _ptr(self.view(gdst, op["w"])),
                      _ptr(self.view(gdst, op["b"])) if op["b"] is not None else 0, _ptr(self.ws), self.ws.numel() * 4,
                      n, op["C"], op["H"], op["W"], op["K"], op["R"], op["S"], op["stride"], op["pad"], s)
                 if i != first_param_op:
                     nxt = self.dbuf[other]
-                    call("clb_conv2d_dgrad", _ptr(d), _ptr(self.view(self.theta, op["w"])), _ptr(nxt),
+                    self._timed(call, "clb_conv2d_dgrad", _ptr(d), _ptr(self.view(self.theta, op["w"])), _ptr(nxt),
                          _ptr(self.wt_ws), n, op["C"], op["H"], op["W"], op["K"], op["R"], op["S"], op["stride"],
                          op["pad"], s)
                     d, other = nxt, other ^ 1

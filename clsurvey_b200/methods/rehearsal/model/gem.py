@@ -97,6 +97,9 @@ class Net(nn.Module):
         for op in eng.ops:
             if op["kind"] == "dropout" and op["module"].training:
                 idx = op["cls_idx"]
+                forced = getattr(self, "forced_masks", None)       # host-drawn masks handed in (parity tests)
+                if forced is not None and idx in forced:
+                    self.dropout_masks[idx] = forced[idx].to(eng.device, torch.float32)
                 if idx not in self.dropout_masks:
                     self.dropout_masks[idx] = (torch.bernoulli(torch.full((op["feat"],), p_retain_unit))
                                                / p_retain_unit).to(eng.device)

@@ -222,10 +222,10 @@ def run_gpu_arm(args):
     sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
     if sampler:
         sampler.start()
-    l0 = eng.n_launch
+    l0 = _capi.lib().clb_launch_count()
     eng.conv_events = []                                # live per-kernel timing of the dominant (conv) launches
     ms = timed(step_dev, args.steps)
-    launches = eng.n_launch - l0
+    launches = _capi.lib().clb_launch_count() - l0
     conv_ms = sum(a.elapsed_time(b) for a, b in eng.conv_events) / max(args.steps, 1)
     n_conv_launch = len(eng.conv_events) // max(args.steps, 1)
     eng.conv_events = None

@@ -21,7 +21,8 @@ SIGNATURES = {
     "clb_sm_count": [c_p],
     "clb_set_matmul_mode": [c_i],
     "clb_get_matmul_mode": [],
-    "clb_conv2d_fwd": [c_p, c_p, c_p, c_p] + [c_i] * 10 + [c_p],
+    "clb_launch_count": [],
+    "clb_conv2d_fwd": [c_p, c_p, c_p, c_p, c_p] + [c_i] * 10 + [c_p],
     "clb_conv2d_dgrad": [c_p, c_p, c_p, c_p] + [c_i] * 9 + [c_p],
     "clb_conv2d_wgrad_ws": [c_i] * 9,
     "clb_conv2d_wgrad": [c_p, c_p, c_p, c_p, c_p, c_sz] + [c_i] * 9 + [c_p],
@@ -50,7 +51,7 @@ SIGNATURES = {
     "clb_nccl_allreduce_f32": [c_p, c_p, c_i64, c_p],
     "clb_nccl_destroy": [c_p],
 }
-_RESTYPE = {"clb_last_error": ctypes.c_char_p, "clb_conv2d_wgrad_ws": c_sz}
+_RESTYPE = {"clb_last_error": ctypes.c_char_p, "clb_conv2d_wgrad_ws": c_sz, "clb_launch_count": ctypes.c_ulonglong}
 
 
 class ClbError(RuntimeError):

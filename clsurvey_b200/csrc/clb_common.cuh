@@ -11,6 +11,8 @@ namespace clb {
 
 void set_error(const char* fmt, ...);
 int sm_count();
+int mm_mode();
+void count_launch();      // every kernel launch of this library is counted (bench.py's gpu_launches)
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -50,5 +52,16 @@ __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+
+
+// tensor-core (tcgen05) path, clb_gemm_tc.cu
+bool tc_conv_supported(int C, int H, int W, int K, int R, int S, int stride, int pad);
+int tc_conv_fwd(const float* x, const float* w2, const float* bias, float* y, int N, int C, int H, int W, int K, int R,
+                int S, int pad, int relu, bool with_lo, cudaStream_t s);
+size_t tc_wgrad_ws_floats(int N, int C, int H, int W, int K, int R, int S);
+int tc_conv_wgrad(const float* x, const float* dy, float* dw, float* ws, int N, int C, int H, int W, int K, int R, int S,
+                  int pad, bool with_lo, cudaStream_t s);
+void tc_permute_w_fwd(const float* w, float* w2, int K, int C, int RS, cudaStream_t s);
+void tc_permute_w_dgrad(const float* w, float* wd, int K, int C, int R, int S, cudaStream_t s);
 
 }  // namespace clb

@@ -27,6 +27,9 @@ int sm_count() {
     return cached;
 }
 int mm_mode() { return g_mm_mode; }
+static unsigned long long g_launches = 0;
+void count_launch() { ++g_launches; }
+unsigned long long launches() { return g_launches; }
 }  // namespace clb
 
 extern "C" {
@@ -46,4 +49,5 @@ int clb_set_matmul_mode(int mode) {
     return CLB_OK;
 }
 int clb_get_matmul_mode(void) { return clb::g_mm_mode; }
+unsigned long long clb_launch_count(void) { return clb::launches(); }
 }

@@ -259,13 +259,13 @@ static inline int gem_grid(int64_t n_vec, int per_sm) {
 template <int K>
 static int launch_dots_gram(const float* g, const float* G, int64_t ld, int64_t P, const int* idx, double* dots,
                             double* gram, cudaStream_t s) {
-    gem_dots_gram_kernel<K><<<gem_grid(P >> 2, 2), kGemThreads, 0, s>>>(g, G, ld, P, idx, dots, gram);
+    gem_dots_gram_kernel<K><<<gem_grid(P >> 2, 2), kGemThreads, 0, s>>>(g, G, ld, P, idx, dots, gram); clb::count_launch();
     return 0;
 }
 template <int K>
 static int launch_project(float* g, const float* G, int64_t ld, int64_t P, const int* idx, const double* v,
                           const int* viol, cudaStream_t s) {
-    gem_project_kernel<K><<<gem_grid(P >> 2, 4), kGemThreads, 0, s>>>(g, G, ld, P, idx, v, viol);
+    gem_project_kernel<K><<<gem_grid(P >> 2, 4), kGemThreads, 0, s>>>(g, G, ld, P, idx, v, viol); clb::count_launch();
     return 0;
 }
 
@@ -301,7 +301,7 @@ int clb_gem_solve_qp(const double* dots, const double* gram, int k, double margi
                      void* stream) {
     CLB_CHECK_ARG(dots && gram && v && viol && k >= 1 && k <= kMaxK);
     const int threads = (1 << k) < 32 ? 32 : (1 << k);
-    gem_qp_kernel<<<1, threads, 0, as_stream(stream)>>>(dots, gram, k, margin, eps, v, viol);
+    gem_qp_kernel<<<1, threads, 0, as_stream(stream)>>>(dots, gram, k, margin, eps, v, viol); clb::count_launch();
     CLB_CHECK_LAUNCH();
     return CLB_OK;
 }

@@ -372,13 +372,13 @@ static int conv_fwd_simt(const float* x, const float* w, const float* bias, floa
     const int64_t tiles128 = (int64_t)((M + 127) / 128) * ((N + 127) / 128);
     if (N <= 32) {
         dim3 grid((M + 127) / 128, (N + 31) / 32, 1);
-        gemm_simt_kernel<8, 2, Im2colPixOuter, StridedMat, true, false, EpiNCHW, true><<<grid, 256, 0, s>>>(A, B, e, Kg, Kg, 0);
+        gemm_simt_kernel<8, 2, Im2colPixOuter, StridedMat, true, false, EpiNCHW, true><<<grid, 256, 0, s>>>(A, B, e, Kg, Kg, 0); clb::count_launch();
     } else if (tiles128 < 2 * sm_count() || N <= 64) {
         dim3 grid((M + 63) / 64, (N + 63) / 64, 1);
-        gemm_simt_kernel<4, 4, Im2colPixOuter, StridedMat, true, false, EpiNCHW, true><<<grid, 256, 0, s>>>(A, B, e, Kg, Kg, 0);
+        gemm_simt_kernel<4, 4, Im2colPixOuter, StridedMat, true, false, EpiNCHW, true><<<grid, 256, 0, s>>>(A, B, e, Kg, Kg, 0); clb::count_launch();
     } else {
         dim3 grid((M + 127) / 128, (N + 127) / 128, 1);
-        gemm_simt_kernel<8, 8, Im2colPixOuter, StridedMat, true, false, EpiNCHW, true><<<grid, 256, 0, s>>>(A, B, e, Kg, Kg, 0);
+        gemm_simt_kernel<8, 8, Im2colPixOuter, StridedMat, true, false, EpiNCHW, true><<<grid, 256, 0, s>>>(A, B, e, Kg, Kg, 0); clb::count_launch();
     }
     return 0;
 }
@@ -405,12 +405,19 @@ using namespace clb;
 
 extern "C" {
 
-int clb_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int N, int C, int H, int W, int K,
-                   int R, int S, int stride, int pad, int relu, void* stream) {
+int clb_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, float* w_ws, int N, int C, int H, int W,
+                   int K, int R, int S, int stride, int pad, int relu, void* stream) {
     CLB_CHECK_ARG(x && w && y && N > 0 && C > 0 && H > 0 && W > 0 && K > 0 && R > 0 && S > 0 && stride > 0 && pad >= 0);
     CLB_CHECK_ARG(H + 2 * pad >= R && W + 2 * pad >= S);
     CLB_CHECK_ARG((int64_t)N * C * H * W < (1LL << 31) && (int64_t)N * K * H * W < (1LL << 31));
     ConvGeom g = make_geom(N, C, H, W, K, R, S, stride, pad);
+    if (mm_mode() != CLB_MM_FP32_SIMT && w_ws != nullptr && tc_conv_supported(C, H, W, K, R, S, stride, pad)) {
+        tc_permute_w_fwd(w, w_ws, K, C, R * S, as_stream(stream));           // [K][C][RS] -> [K][RS][C]
+        int rc = tc_conv_fwd(x, w_ws, bias, y, N, C, H, W, K, R, S, pad, relu, mm_mode() == CLB_MM_TF32X3, as_stream(stream));
+        if (rc) return rc;
+        CLB_CHECK_LAUNCH();
+        return CLB_OK;
+    }
     conv_fwd_simt(x, w, bias, y, g, relu, as_stream(stream));
     CLB_CHECK_LAUNCH();
     return CLB_OK;
@@ -421,12 +428,20 @@ int clb_conv2d_dgrad(const float* dy, const float* w, float* dx, float* wt_ws, i
     CLB_CHECK_ARG(dy && w && dx && N > 0 && C > 0 && H > 0 && W > 0 && K > 0 && R > 0 && S > 0 && stride > 0 && pad >= 0);
     cudaStream_t s = as_stream(stream);
     ConvGeom g = make_geom(N, C, H, W, K, R, S, stride, pad);
+    if (mm_mode() != CLB_MM_FP32_SIMT && wt_ws != nullptr && R - 1 - pad >= 0 &&
+        tc_conv_supported(C, H, W, K, R, S, stride, pad) && tc_conv_supported(K, g.P, g.Q, C, R, S, 1, R - 1 - pad)) {
+        tc_permute_w_dgrad(w, wt_ws, K, C, R, S, s);                          // [K][C][R][S] -> [C][flipped RS][K]
+        int rc = tc_conv_fwd(dy, wt_ws, nullptr, dx, N, K, g.P, g.Q, C, R, S, R - 1 - pad, 0, mm_mode() == CLB_MM_TF32X3, s);
+        if (rc) return rc;
+        CLB_CHECK_LAUNCH();
+        return CLB_OK;
+    }
     if (stride == 1 && R - 1 - pad >= 0 && S - 1 - pad >= 0 && R == S) {
         CLB_CHECK_ARG(wt_ws != nullptr);
         const int64_t total = (int64_t)K * C * R * S;
         int blocks = (int)((total + 255) / 256);
         if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-        flip_transpose_weights_kernel<<<blocks, 256, 0, s>>>(w, wt_ws, K, C, R, S);
+        flip_transpose_weights_kernel<<<blocks, 256, 0, s>>>(w, wt_ws, K, C, R, S); clb::count_launch();
         // forward conv over dY: input [N, K, P, Q], output [N, C, H, W], pad' = R-1-pad
         ConvGeom gd = make_geom(N, K, g.P, g.Q, C, R, S, 1, R - 1 - pad);
         CLB_CHECK_ARG(gd.P == H && gd.Q == W);
@@ -435,7 +450,7 @@ int clb_conv2d_dgrad(const float* dy, const float* w, float* dx, float* wt_ws, i
         const int64_t total = (int64_t)N * C * H * W;
         int blocks = (int)((total + 255) / 256);
         if (blocks > sm_count() * 16) blocks = sm_count() * 16;
-        conv_dgrad_naive_kernel<<<blocks, 256, 0, s>>>(dy, w, dx, g);
+        conv_dgrad_naive_kernel<<<blocks, 256, 0, s>>>(dy, w, dx, g); clb::count_launch();
     }
     CLB_CHECK_LAUNCH();
     return CLB_OK;
@@ -445,7 +460,12 @@ size_t clb_conv2d_wgrad_ws(int N, int C, int H, int W, int K, int R, int S, int 
     ConvGeom g = make_geom(N, C, H, W, K, R, S, stride, pad);
     int splits, chunk, bm;
     wgrad_plan(g, &splits, &chunk, &bm);
-    return (size_t)splits * K * C * R * S * sizeof(float);
+    size_t need = (size_t)splits * K * C * R * S * sizeof(float);
+    if (tc_conv_supported(C, H, W, K, R, S, stride, pad)) {
+        const size_t t = tc_wgrad_ws_floats(N, C, H, W, K, R, S) * sizeof(float);
+        if (t > need) need = t;
+    }
+    return need;
 }
 
 int clb_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias, float* ws, size_t ws_bytes, int N, int C,
@@ -455,6 +475,21 @@ int clb_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias, f
     cudaStream_t s = as_stream(stream);
     ConvGeom g = make_geom(N, C, H, W, K, R, S, stride, pad);
     const int M = K, Ng = C * R * S, Kg = N * g.P * g.Q;
+    if (mm_mode() != CLB_MM_FP32_SIMT && tc_conv_supported(C, H, W, K, R, S, stride, pad)) {
+        const size_t tneed = tc_wgrad_ws_floats(N, C, H, W, K, R, S) * sizeof(float);
+        if (ws == nullptr || ws_bytes < tneed) {
+            set_error("clb_conv2d_wgrad: workspace %zu bytes < required %zu", ws_bytes, tneed);
+            return CLB_EWORKSPACE;
+        }
+        int rc = tc_conv_wgrad(x, dy, dw, ws, N, C, H, W, K, R, S, pad, mm_mode() == CLB_MM_TF32X3, s);
+        if (rc) return rc;
+        CLB_CHECK_LAUNCH();
+        if (dbias) {
+            conv_bias_grad_kernel<<<K, 256, 0, s>>>(dy, dbias, N, K, g.P * g.Q); clb::count_launch();
+            CLB_CHECK_LAUNCH();
+        }
+        return CLB_OK;
+    }
     int splits, chunk, bm;
     wgrad_plan(g, &splits, &chunk, &bm);
     const size_t need = (size_t)splits * M * Ng * sizeof(float);
@@ -468,22 +503,22 @@ int clb_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias, f
     if (bm == 128) {
         dim3 grid((M + 127) / 128, (Ng + 127) / 128, splits);
         gemm_simt_kernel<8, 8, DyKoutOuter, Im2colCrsOuter, false, false, EpiRM, false><<<grid, 256, 0, s>>>(
-            A, B, e, Kg, chunk, (int64_t)M * Ng);
+            A, B, e, Kg, chunk, (int64_t)M * Ng); clb::count_launch();
     } else {
         dim3 grid((M + 63) / 64, (Ng + 63) / 64, splits);
         gemm_simt_kernel<4, 4, DyKoutOuter, Im2colCrsOuter, false, false, EpiRM, false><<<grid, 256, 0, s>>>(
-            A, B, e, Kg, chunk, (int64_t)M * Ng);
+            A, B, e, Kg, chunk, (int64_t)M * Ng); clb::count_launch();
     }
     CLB_CHECK_LAUNCH();
     if (splits > 1) {
         const int64_t n = (int64_t)M * Ng;
         int blocks = (int)((n + 255) / 256);
         if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-        splitk_reduce_kernel<<<blocks, 256, 0, s>>>(ws, dw, n, splits);
+        splitk_reduce_kernel<<<blocks, 256, 0, s>>>(ws, dw, n, splits); clb::count_launch();
         CLB_CHECK_LAUNCH();
     }
     if (dbias) {
-        conv_bias_grad_kernel<<<K, 256, 0, s>>>(dy, dbias, N, K, g.P * g.Q);
+        conv_bias_grad_kernel<<<K, 256, 0, s>>>(dy, dbias, N, K, g.P * g.Q); clb::count_launch();
         CLB_CHECK_LAUNCH();
     }
     return CLB_OK;
@@ -498,10 +533,10 @@ int clb_linear_fwd(const float* x, const float* w, const float* bias, float* y, 
     EpiRM e; e.c = y; e.ldc = out; e.bias = bias; e.relu = relu; e.M = M; e.N = out;
     if (out <= 32) {
         dim3 grid((M + 127) / 128, (out + 31) / 32, 1);
-        gemm_simt_kernel<8, 2, StridedMat, StridedMat, false, false, EpiRM, false><<<grid, 256, 0, s>>>(A, B, e, in, in, 0);
+        gemm_simt_kernel<8, 2, StridedMat, StridedMat, false, false, EpiRM, false><<<grid, 256, 0, s>>>(A, B, e, in, in, 0); clb::count_launch();
     } else {
         dim3 grid((M + 63) / 64, (out + 63) / 64, 1);
-        gemm_simt_kernel<4, 4, StridedMat, StridedMat, false, false, EpiRM, false><<<grid, 256, 0, s>>>(A, B, e, in, in, 0);
+        gemm_simt_kernel<4, 4, StridedMat, StridedMat, false, false, EpiRM, false><<<grid, 256, 0, s>>>(A, B, e, in, in, 0); clb::count_launch();
     }
     CLB_CHECK_LAUNCH();
     return CLB_OK;
@@ -514,7 +549,7 @@ int clb_linear_dgrad(const float* dy, const float* w, float* dx, int M, int in, 
     StridedMat B{w, 1, in, in, out};         // element(n = i, k = o) = w[o*in + i]
     EpiRM e; e.c = dx; e.ldc = in; e.bias = nullptr; e.relu = 0; e.M = M; e.N = in;
     dim3 grid((M + 63) / 64, (in + 63) / 64, 1);
-    gemm_simt_kernel<4, 4, StridedMat, StridedMat, false, true, EpiRM, false><<<grid, 256, 0, s>>>(A, B, e, out, out, 0);
+    gemm_simt_kernel<4, 4, StridedMat, StridedMat, false, true, EpiRM, false><<<grid, 256, 0, s>>>(A, B, e, out, out, 0); clb::count_launch();
     CLB_CHECK_LAUNCH();
     return CLB_OK;
 }
@@ -527,14 +562,14 @@ int clb_linear_wgrad(const float* x, const float* dy, float* dw, float* dbias, i
     EpiRM e; e.c = dw; e.ldc = in; e.bias = nullptr; e.relu = 0; e.M = out; e.N = in;
     if (out <= 32) {
         dim3 grid((out + 31) / 32, (in + 127) / 128, 1);
-        gemm_simt_kernel<2, 8, StridedMat, StridedMat, true, true, EpiRM, false><<<grid, 256, 0, s>>>(A, B, e, M, M, 0);
+        gemm_simt_kernel<2, 8, StridedMat, StridedMat, true, true, EpiRM, false><<<grid, 256, 0, s>>>(A, B, e, M, M, 0); clb::count_launch();
     } else {
         dim3 grid((out + 63) / 64, (in + 63) / 64, 1);
-        gemm_simt_kernel<4, 4, StridedMat, StridedMat, true, true, EpiRM, false><<<grid, 256, 0, s>>>(A, B, e, M, M, 0);
+        gemm_simt_kernel<4, 4, StridedMat, StridedMat, true, true, EpiRM, false><<<grid, 256, 0, s>>>(A, B, e, M, M, 0); clb::count_launch();
     }
     CLB_CHECK_LAUNCH();
     if (dbias) {
-        linear_bias_grad_kernel<<<(out + 127) / 128, 128, 0, s>>>(dy, dbias, M, out);
+        linear_bias_grad_kernel<<<(out + 127) / 128, 128, 0, s>>>(dy, dbias, M, out); clb::count_launch();
         CLB_CHECK_LAUNCH();
     }
     return CLB_OK;

@@ -159,7 +159,8 @@ softmax_loss_kernel(const float* __restrict__ logits, int ld, int col_off, int n
             for (int c = 0; c < ncols; ++c) se += expf(z[c] - mx);
             const float lse = logf(se);
             const float scale = (mode == CLB_LOSS_MEAN_CE) ? 1.0f / denom : 1.0f;
-            my_loss += -((z[y] - mx) - lse);
+            const bool y_ok = (y >= 0 && y < ncols);          // out-of-range label: poison the loss, never read OOB
+            my_loss += y_ok ? -((z[y] - mx) - lse) : __int_as_float(0x7fc00000);
             if (dz) {
                 for (int c = 0; c < ncols; ++c) {
                     const float p = expf((z[c] - mx) - lse);
@@ -198,7 +199,7 @@ int clb_relu_bwd(const float* dy, const float* y, float* dx, int64_t n, void* st
     CLB_CHECK_ARG(dy && y && dx && n >= 0);
     CLB_CHECK_ARG((((uintptr_t)dy | (uintptr_t)y | (uintptr_t)dx) & 15) == 0);
     if (n == 0) return CLB_OK;
-    relu_bwd_kernel<<<ew_grid(n >> 2, 256), 256, 0, as_stream(stream)>>>(dy, y, dx, n);
+    relu_bwd_kernel<<<ew_grid(n >> 2, 256), 256, 0, as_stream(stream)>>>(dy, y, dx, n); clb::count_launch();
     CLB_CHECK_LAUNCH();
     return CLB_OK;
 }
@@ -208,7 +209,7 @@ int clb_maxpool_fwd(const float* x, float* y, uint8_t* argmax, int N, int C, int
     CLB_CHECK_ARG(x && y && argmax && N > 0 && C > 0 && k >= 1 && k <= 15 && stride >= 1 && H >= k && W >= k);
     const int PH = (H - k) / stride + 1, PW = (W - k) / stride + 1;
     const int64_t total = (int64_t)N * C * PH * PW;
-    maxpool_fwd_kernel<<<ew_grid(total, 256), 256, 0, as_stream(stream)>>>(x, y, argmax, total, H, W, PH, PW, k, stride);
+    maxpool_fwd_kernel<<<ew_grid(total, 256), 256, 0, as_stream(stream)>>>(x, y, argmax, total, H, W, PH, PW, k, stride); clb::count_launch();
     CLB_CHECK_LAUNCH();
     return CLB_OK;
 }
@@ -219,7 +220,7 @@ int clb_maxpool_bwd(const float* dy, const uint8_t* argmax, const float* x_relu_
     const int PH = (H - k) / stride + 1, PW = (W - k) / stride + 1;
     const int64_t total = (int64_t)N * C * H * W;
     maxpool_bwd_kernel<<<ew_grid(total, 256), 256, 0, as_stream(stream)>>>(dy, argmax, x_relu_out, dx, total, H, W, PH,
-                                                                            PW, k, stride);
+                                                                            PW, k, stride); clb::count_launch();
     CLB_CHECK_LAUNCH();
     return CLB_OK;
 }
@@ -227,14 +228,14 @@ int clb_maxpool_bwd(const float* dy, const uint8_t* argmax, const float* x_relu_
 int clb_adaptive_avgpool_fwd(const float* x, float* y, int N, int C, int H, int W, int OH, int OW, void* stream) {
     CLB_CHECK_ARG(x && y && N > 0 && C > 0 && H > 0 && W > 0 && OH > 0 && OW > 0);
     const int64_t total = (int64_t)N * C * OH * OW;
-    aavgpool_fwd_kernel<<<ew_grid(total, 256), 256, 0, as_stream(stream)>>>(x, y, total, H, W, OH, OW);
+    aavgpool_fwd_kernel<<<ew_grid(total, 256), 256, 0, as_stream(stream)>>>(x, y, total, H, W, OH, OW); clb::count_launch();
     CLB_CHECK_LAUNCH();
     return CLB_OK;
 }
 int clb_adaptive_avgpool_bwd(const float* dy, float* dx, int N, int C, int H, int W, int OH, int OW, void* stream) {
     CLB_CHECK_ARG(dy && dx && N > 0 && C > 0 && H > 0 && W > 0 && OH > 0 && OW > 0);
     const int64_t total = (int64_t)N * C * H * W;
-    aavgpool_bwd_kernel<<<ew_grid(total, 256), 256, 0, as_stream(stream)>>>(dy, dx, total, H, W, OH, OW);
+    aavgpool_bwd_kernel<<<ew_grid(total, 256), 256, 0, as_stream(stream)>>>(dy, dx, total, H, W, OH, OW); clb::count_launch();
     CLB_CHECK_LAUNCH();
     return CLB_OK;
 }
@@ -242,7 +243,7 @@ int clb_adaptive_avgpool_bwd(const float* dy, float* dx, int N, int C, int H, in
 int clb_mask_mul(const float* x, const float* mask, float* y, int rows, int cols, int mask_rows, void* stream) {
     CLB_CHECK_ARG(x && mask && y && rows > 0 && cols > 0 && (mask_rows == 1 || mask_rows == rows));
     const int64_t total = (int64_t)rows * cols;
-    mask_mul_kernel<<<ew_grid(total, 256), 256, 0, as_stream(stream)>>>(x, mask, y, total, cols, mask_rows == 1 && rows != 1);
+    mask_mul_kernel<<<ew_grid(total, 256), 256, 0, as_stream(stream)>>>(x, mask, y, total, cols, mask_rows == 1 && rows != 1); clb::count_launch();
     CLB_CHECK_LAUNCH();
     return CLB_OK;
 }
@@ -254,7 +255,7 @@ int clb_softmax_loss(const float* logits, int ld, int col_off, int ncols, const 
     CLB_CHECK_ARG(mode == CLB_LOSS_SUM_SQ || labels != nullptr);
     CLB_CHECK_ARG(mode != CLB_LOSS_MEAN_CE || mean_denominator > 0.f);
     softmax_loss_kernel<<<1, kLossThreads, 0, as_stream(stream)>>>(logits, ld, col_off, ncols, labels, B, mode,
-                                                                    mean_denominator, loss_out, correct_out, dlogits);
+                                                                    mean_denominator, loss_out, correct_out, dlogits); clb::count_launch();
     CLB_CHECK_LAUNCH();
     return CLB_OK;
 }

@@ -235,7 +235,7 @@ int clb_sgd_penalty_step(float* theta, const float* g, const float* omega, const
     if (n == 0) return CLB_OK;
     SgdArgs a{two_lambda, lr, momentum, weight_decay, grad_scale, first_step ? 1 : 0};
     sgd_penalty_kernel<<<stream_grid(n >> 2), kThreads, 0, as_stream(stream)>>>(theta, g, omega, theta_star, buf, n,
-                                                                                 n_penalised, a);
+                                                                                 n_penalised, a); clb::count_launch();
     CLB_CHECK_LAUNCH();
     return CLB_OK;
 }
@@ -248,7 +248,7 @@ int clb_si_step(float* theta, const float* g, const float* omega, const float* t
                   aligned16(w));
     if (n == 0) return CLB_OK;
     SgdArgs a{two_lambda, lr, momentum, weight_decay, grad_scale, first_step ? 1 : 0};
-    si_step_kernel<<<stream_grid(n >> 2), kThreads, 0, as_stream(stream)>>>(theta, g, omega, theta_star, buf, w, n, a);
+    si_step_kernel<<<stream_grid(n >> 2), kThreads, 0, as_stream(stream)>>>(theta, g, omega, theta_star, buf, w, n, a); clb::count_launch();
     CLB_CHECK_LAUNCH();
     return CLB_OK;
 }
@@ -256,7 +256,7 @@ int clb_si_step(float* theta, const float* g, const float* omega, const float* t
 int clb_fisher_accum(float* omega, const float* g, float data_len, int64_t n, void* stream) {
     CLB_CHECK_ARG(omega && g && n >= 0 && data_len > 0 && aligned16(omega) && aligned16(g));
     if (n == 0) return CLB_OK;
-    fisher_kernel<<<stream_grid(n >> 2), kThreads, 0, as_stream(stream)>>>(omega, g, data_len, n);
+    fisher_kernel<<<stream_grid(n >> 2), kThreads, 0, as_stream(stream)>>>(omega, g, data_len, n); clb::count_launch();
     CLB_CHECK_LAUNCH();
     return CLB_OK;
 }
@@ -264,7 +264,7 @@ int clb_fisher_accum(float* omega, const float* g, float data_len, int64_t n, vo
 int clb_mas_accum(float* omega, const float* g, float prev_size, float curr_size, int64_t n, void* stream) {
     CLB_CHECK_ARG(omega && g && n >= 0 && curr_size > 0 && aligned16(omega) && aligned16(g));
     if (n == 0) return CLB_OK;
-    mas_kernel<<<stream_grid(n >> 2), kThreads, 0, as_stream(stream)>>>(omega, g, prev_size, curr_size, n);
+    mas_kernel<<<stream_grid(n >> 2), kThreads, 0, as_stream(stream)>>>(omega, g, prev_size, curr_size, n); clb::count_launch();
     CLB_CHECK_LAUNCH();
     return CLB_OK;
 }
@@ -275,7 +275,7 @@ int clb_si_consolidate(float* omega, float* w, const float* theta, float* theta_
     CLB_CHECK_ARG(aligned16(omega) && aligned16(w) && aligned16(theta) && aligned16(theta_star));
     if (n == 0) return CLB_OK;
     si_consolidate_kernel<<<stream_grid(n >> 2), kThreads, 0, as_stream(stream)>>>(omega, w, theta, theta_star, slack,
-                                                                                    n);
+                                                                                    n); clb::count_launch();
     CLB_CHECK_LAUNCH();
     return CLB_OK;
 }
@@ -283,7 +283,7 @@ int clb_si_consolidate(float* omega, float* w, const float* theta, float* theta_
 int clb_axpby(float* dst, const float* a, const float* b, float scale_b, int64_t n, void* stream) {
     CLB_CHECK_ARG(dst && a && b && n >= 0 && aligned16(dst) && aligned16(a) && aligned16(b));
     if (n == 0) return CLB_OK;
-    axpby_kernel<<<stream_grid(n >> 2), kThreads, 0, as_stream(stream)>>>(dst, a, b, scale_b, n);
+    axpby_kernel<<<stream_grid(n >> 2), kThreads, 0, as_stream(stream)>>>(dst, a, b, scale_b, n); clb::count_launch();
     CLB_CHECK_LAUNCH();
     return CLB_OK;
 }

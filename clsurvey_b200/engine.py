@@ -249,8 +249,9 @@ class Engine:
             k = op["kind"]
             if k == "conv":
                 self._timed(call, "clb_conv2d_fwd", _ptr(cur), _ptr(self.view(self.theta, op["w"])),
-                     _ptr(self.view(self.theta, op["b"])) if op["b"] is not None else 0, _ptr(op["out"]), n, op["C"],
-                     op["H"], op["W"], op["K"], op["R"], op["S"], op["stride"], op["pad"], int(op["relu"]), s)
+                     _ptr(self.view(self.theta, op["b"])) if op["b"] is not None else 0, _ptr(op["out"]),
+                     _ptr(self.wt_ws), n, op["C"], op["H"], op["W"], op["K"], op["R"], op["S"], op["stride"], op["pad"],
+                     int(op["relu"]), s)
                 cur = op["out"]
             elif k == "maxpool":
                 call("clb_maxpool_fwd", _ptr(cur), _ptr(op["out"]), _ptr(op["argmax"]), n, op["C"], op["H"], op["W"],

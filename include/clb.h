@@ -47,14 +47,16 @@ int clb_version(void);
 int clb_sm_count(int* out);
 int clb_set_matmul_mode(int mode);
 int clb_get_matmul_mode(void);
+unsigned long long clb_launch_count(void); /* kernels launched by this library so far (process-wide) */
 
 /* ------------------------------------------------------------------------------------------
  * Layer kernels (a2, a3).  Replace model(inputs) / loss.backward() of train_EWC.py:181-187.
  * ---------------------------------------------------------------------------------------- */
 
-/* y = conv2d(x, w) + bias, optional fused ReLU.  nn.Conv2d + nn.ReLU  (models/VGGSlim.py:34-38) */
-int clb_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int N, int C, int H, int W, int K,
-                   int R, int S, int stride, int pad, int relu, void* stream);
+/* y = conv2d(x, w) + bias, optional fused ReLU.  nn.Conv2d + nn.ReLU  (models/VGGSlim.py:34-38)
+ * w_ws: scratch of K*C*R*S floats for the tensor-core path's re-ordered weights (may be NULL: forces the fp32 path) */
+int clb_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, float* w_ws, int N, int C, int H,
+                   int W, int K, int R, int S, int stride, int pad, int relu, void* stream);
 /* dx = conv2d_backward_input(dy, w).  wt_ws: scratch of K*C*R*S floats (transposed/flipped weights). */
 int clb_conv2d_dgrad(const float* dy, const float* w, float* dx, float* wt_ws, int N, int C, int H, int W, int K,
                      int R, int S, int stride, int pad, void* stream);

@@ -116,8 +116,9 @@ def test_conv2d_fwd_bwd(capi, shape, mode):
         y_ = dev(torch.zeros_like(y_ref))
         dxc, dwc, dyc = dev(x), dev(w), dev(dy)
         dbc = dev(b)
-        capi.call("clb_conv2d_fwd", dxc.data_ptr(), dwc.data_ptr(), dbc.data_ptr(), y_.data_ptr(), N, C, H, W, K, R, R,
-                  stride, pad, 1, S())
+        wws = torch.empty(w.numel(), device="cuda")
+        capi.call("clb_conv2d_fwd", dxc.data_ptr(), dwc.data_ptr(), dbc.data_ptr(), y_.data_ptr(), wws.data_ptr(), N, C, H,
+                  W, K, R, R, stride, pad, 1, S())
         assert rel_err(y_, y_ref) <= tol
         ws_bytes = capi.lib().clb_conv2d_wgrad_ws(N, C, H, W, K, R, R, stride, pad)
         ws = torch.empty(ws_bytes // 4 + 4, device="cuda")
@@ -174,9 +175,10 @@ def test_maxpool_relu(capi, N, C, H, W, k, s):
     capi.call("clb_maxpool_fwd", dxd.data_ptr(), y_.data_ptr(), am.data_ptr(), N, C, H, W, k, s, S())
     assert torch.equal(y_.cpu(), y_ref.detach())
     gx = torch.zeros(N, C, H, W, device="cuda")
-    capi.call("clb_maxpool_bwd", dev(dy).data_ptr(), am.data_ptr(), 0, gx.data_ptr(), N, C, H, W, k, s, S())
+    dyd = dev(dy)
+    capi.call("clb_maxpool_bwd", dyd.data_ptr(), am.data_ptr(), 0, gx.data_ptr(), N, C, H, W, k, s, S())
     assert rel_err(gx, x.grad) <= 1e-6
-    capi.call("clb_maxpool_bwd", dev(dy).data_ptr(), am.data_ptr(), dxd.data_ptr(), gx.data_ptr(), N, C, H, W, k, s, S())
+    capi.call("clb_maxpool_bwd", dyd.data_ptr(), am.data_ptr(), dxd.data_ptr(), gx.data_ptr(), N, C, H, W, k, s, S())
     assert rel_err(gx, dx_relu) <= 1e-6
     d2 = dev(dy.new_ones(x.shape))
     capi.call("clb_relu_bwd", d2.data_ptr(), dxd.data_ptr(), d2.data_ptr(), x.numel(), S())
@@ -189,19 +191,22 @@ def test_avgpool_and_mask(capi):
     dy = torch.randn_like(y)
     y.backward(dy)
     y_, gx = torch.zeros(3, 4, 6, 6, device="cuda"), torch.zeros(3, 4, 1, 1, device="cuda")
-    capi.call("clb_adaptive_avgpool_fwd", dev(x.detach()).data_ptr(), y_.data_ptr(), 3, 4, 1, 1, 6, 6, S())
-    capi.call("clb_adaptive_avgpool_bwd", dev(dy).data_ptr(), gx.data_ptr(), 3, 4, 1, 1, 6, 6, S())
+    xd, dyd = dev(x.detach()), dev(dy)
+    capi.call("clb_adaptive_avgpool_fwd", xd.data_ptr(), y_.data_ptr(), 3, 4, 1, 1, 6, 6, S())
+    capi.call("clb_adaptive_avgpool_bwd", dyd.data_ptr(), gx.data_ptr(), 3, 4, 1, 1, 6, 6, S())
     assert rel_err(y_, y) <= 1e-7 and rel_err(gx, x.grad) <= 1e-6
     x2 = torch.randn(2, 3, 13, 13).requires_grad_()
     y2 = F.adaptive_avg_pool2d(x2, (6, 6))
     y2.backward(torch.ones_like(y2))
     y2_, gx2 = torch.zeros(2, 3, 6, 6, device="cuda"), torch.zeros(2, 3, 13, 13, device="cuda")
-    capi.call("clb_adaptive_avgpool_fwd", dev(x2.detach()).data_ptr(), y2_.data_ptr(), 2, 3, 13, 13, 6, 6, S())
-    capi.call("clb_adaptive_avgpool_bwd", dev(torch.ones_like(y2)).data_ptr(), gx2.data_ptr(), 2, 3, 13, 13, 6, 6, S())
+    x2d, o2d = dev(x2.detach()), dev(torch.ones_like(y2))
+    capi.call("clb_adaptive_avgpool_fwd", x2d.data_ptr(), y2_.data_ptr(), 2, 3, 13, 13, 6, 6, S())
+    capi.call("clb_adaptive_avgpool_bwd", o2d.data_ptr(), gx2.data_ptr(), 2, 3, 13, 13, 6, 6, S())
     assert rel_err(y2_, y2) <= 1e-6 and rel_err(gx2, x2.grad) <= 1e-6
     a, m = torch.randn(7, 33), (torch.rand(33) > 0.5).float() * 2
     out = torch.zeros(7, 33, device="cuda")
-    capi.call("clb_mask_mul", dev(a).data_ptr(), dev(m).data_ptr(), out.data_ptr(), 7, 33, 1, S())
+    ad, md = dev(a), dev(m)
+    capi.call("clb_mask_mul", ad.data_ptr(), md.data_ptr(), out.data_ptr(), 7, 33, 1, S())
     assert torch.equal(out.cpu(), a * m)
 
 
@@ -217,7 +222,8 @@ def test_softmax_loss_modes(capi, B, ld, off, nc):
         loss = torch.zeros(1, device="cuda")
         corr = torch.zeros(1, dtype=torch.int32, device="cuda")
         dz = torch.full((B, ld), 7.0, device="cuda")
-        capi.call("clb_softmax_loss", dev(z.detach()).data_ptr(), ld, off, nc, dev(y).data_ptr(), B, mode, float(B),
+        zd, yd = dev(z.detach()), dev(y)                      # keep references: the allocator recycles temporaries
+        capi.call("clb_softmax_loss", zd.data_ptr(), ld, off, nc, yd.data_ptr(), B, mode, float(B),
                   loss.data_ptr(), corr.data_ptr(), dz.data_ptr(), S())
         assert abs(loss.item() - loss_ref.item()) <= 2e-6 * abs(loss_ref.item())
         assert rel_err(dz, z.grad) <= 2e-6

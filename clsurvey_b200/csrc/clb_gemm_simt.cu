@@ -289,15 +289,28 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __rest
     }
 }
 
-// dbias[k] = sum over (img, pq) of dy[img][k][pq]; one CTA per channel, fixed-order tree reduction
-__global__ void __launch_bounds__(256) conv_bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ db, int N,
-                                                             int K, int PQ) {
-    const int k = blockIdx.x;
+// dbias[k] = sum over (img, pq) of dy[img][k][pq].  Two deterministic stages: grid (K, nsplit) CTAs each reduce a
+// contiguous range of images of one channel (float4 loads, fixed-order tree), then the first nsplit partials are summed
+// in order by the last stage.  No atomics: bit-reproducible.
+__global__ void __launch_bounds__(256) conv_bias_grad_partial_kernel(const float* __restrict__ dy, float* __restrict__ part,
+                                                                     int N, int K, int PQ, int imgs_per_split) {
+    const int k = blockIdx.x, sp = blockIdx.y;
+    const int n0 = sp * imgs_per_split, n1 = min(N, n0 + imgs_per_split);
     float s = 0.f;
-    const int total = N * PQ;
-    for (int i = threadIdx.x; i < total; i += 256) {
-        const int img = i / PQ, pq = i - img * PQ;
-        s += dy[((int64_t)img * K + k) * PQ + pq];
+    if ((PQ & 3) == 0) {
+        const int pq4 = PQ >> 2;
+        const int total = (n1 - n0) * pq4;
+        for (int i = threadIdx.x; i < total; i += 256) {
+            const int img = n0 + i / pq4, q = i - (i / pq4) * pq4;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(dy + ((int64_t)img * K + k) * PQ) + q);
+            s += (v.x + v.y) + (v.z + v.w);
+        }
+    } else {
+        const int total = (n1 - n0) * PQ;
+        for (int i = threadIdx.x; i < total; i += 256) {
+            const int img = n0 + i / PQ, pq = i - (i / PQ) * PQ;
+            s += dy[((int64_t)img * K + k) * PQ + pq];
+        }
     }
     __shared__ float red[256];
     red[threadIdx.x] = s;
@@ -306,7 +319,27 @@ __global__ void __launch_bounds__(256) conv_bias_grad_kernel(const float* __rest
         if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) db[k] = red[0];
+    if (threadIdx.x == 0) part[(int64_t)sp * K + k] = red[0];
+}
+__global__ void conv_bias_grad_final_kernel(const float* __restrict__ part, float* __restrict__ db, int K, int nsplit) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    float s = part[k];
+    for (int sp = 1; sp < nsplit; ++sp) s += part[(int64_t)sp * K + k];
+    db[k] = s;
+}
+static inline int bias_grad_splits(int N, int K) {
+    int want = (4 * 148 + K - 1) / K;            // ~4 CTAs per SM (fixed 148 => device-independent summation order)
+    if (want > N) want = N;
+    if (want > 64) want = 64;
+    return want < 1 ? 1 : want;
+}
+// scratch: bias_grad_splits(N,K) * K floats, taken from the tail of the wgrad workspace
+static void conv_bias_grad(const float* dy, float* db, float* scratch, int N, int K, int PQ, cudaStream_t s) {
+    const int want = bias_grad_splits(N, K);
+    const int per = (N + want - 1) / want, nsplit = (N + per - 1) / per;
+    conv_bias_grad_partial_kernel<<<dim3(K, nsplit), 256, 0, s>>>(dy, scratch, N, K, PQ, per); clb::count_launch();
+    conv_bias_grad_final_kernel<<<(K + 127) / 128, 128, 0, s>>>(scratch, db, K, nsplit); clb::count_launch();
 }
 
 __global__ void linear_bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ db, int M, int out) {
@@ -465,7 +498,7 @@ size_t clb_conv2d_wgrad_ws(int N, int C, int H, int W, int K, int R, int S, int 
         const size_t t = tc_wgrad_ws_floats(N, C, H, W, K, R, S) * sizeof(float);
         if (t > need) need = t;
     }
-    return need;
+    return need + (size_t)64 * K * sizeof(float);           // + bias-gradient partials
 }
 
 int clb_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias, float* ws, size_t ws_bytes, int N, int C,
@@ -485,7 +518,8 @@ int clb_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias, f
         if (rc) return rc;
         CLB_CHECK_LAUNCH();
         if (dbias) {
-            conv_bias_grad_kernel<<<K, 256, 0, s>>>(dy, dbias, N, K, g.P * g.Q); clb::count_launch();
+            if (ws_bytes < tneed + (size_t)64 * K * sizeof(float)) { set_error("clb_conv2d_wgrad: workspace too small for bias partials"); return CLB_EWORKSPACE; }
+            conv_bias_grad(dy, dbias, ws + tneed / sizeof(float), N, K, g.P * g.Q, s);
             CLB_CHECK_LAUNCH();
         }
         return CLB_OK;
@@ -518,7 +552,9 @@ int clb_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias, f
         CLB_CHECK_LAUNCH();
     }
     if (dbias) {
-        conv_bias_grad_kernel<<<K, 256, 0, s>>>(dy, dbias, N, K, g.P * g.Q); clb::count_launch();
+        const size_t off = splits > 1 ? need : 0;
+        if (ws == nullptr || ws_bytes < off + (size_t)64 * K * sizeof(float)) { set_error("clb_conv2d_wgrad: workspace too small for bias partials"); return CLB_EWORKSPACE; }
+        conv_bias_grad(dy, dbias, ws + off / sizeof(float), N, K, g.P * g.Q, s);
         CLB_CHECK_LAUNCH();
     }
     return CLB_OK;

@@ -16,98 +16,14 @@
 //
 // Warp roles (288 threads): warps 0-3 load even K blocks, warps 4-7 load odd K blocks (two groups keep two blocks of
 // global loads in flight), warp 8 allocates TMEM and issues the MMAs; warps 0-7 then run the epilogue.
-#include "clb_common.cuh"
+#include <stdlib.h>
+
+#include "clb_tc_ptx.cuh"
 
 namespace clb {
 namespace tc {
 
-constexpr int BM = 128;
-constexpr int BK = 32;                 // fp32 elements per K block = one 128-byte swizzle row
-constexpr int kLoaderThreads = 256;
 constexpr int kThreads = 288;
-constexpr uint32_t kHiMask = 0xFFFFE000u;
-
-struct FastDiv32 {
-    uint32_t d, magic, shift;
-    FastDiv32() : d(1), magic(0), shift(0) {}
-    explicit FastDiv32(uint32_t dd) : d(dd) {
-        if (dd <= 1) { d = 1; magic = 0; shift = 0; return; }
-        shift = 0;
-        while ((1ull << shift) < dd) ++shift;
-        magic = (uint32_t)(((1ull << 32) * ((1ull << shift) - dd)) / dd + 1);
-    }
-    __device__ __forceinline__ uint32_t div(uint32_t n) const {
-        return d == 1 ? n : (uint32_t)(((uint64_t)__umulhi(n, magic) + n) >> shift);
-    }
-};
-
-// ---------------------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, M=128, N from idesc, K=8
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"): 8-row core groups 1024 B apart.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    const uint64_t lo = (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16);          // start addr, LBO (ignored) = 1
-    const uint64_t hi = (uint64_t)(1024u >> 4) | ((uint64_t)1 << 14) | ((uint64_t)2 << 29);  // SBO=1024B, version=1, SW128
-    return lo | (hi << 32);
-}
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
 
 // store one 4-float chunk (row r, 16-byte chunk c) of a K block into the swizzled hi / lo tiles
 template <bool WITH_LO>
@@ -279,7 +195,11 @@ gemm_tc_kernel(ALoad A, BLoad B, Epi epi, int num_kb_total, int kb_per_split) {
         mbar_init(bar_tmem, 1);
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(tmem_slot, BN);
+    // two accumulators when splitting: columns [0,BN) take hi*hi, columns [BN,2BN) take the ~2^-11 smaller cross terms.
+    // The tensor core's fp32 accumulate truncates; keeping the small terms apart cuts the number of (biased) roundings
+    // applied to the large accumulator by 3x.
+    constexpr uint32_t kTmemCols = WITH_LO ? 2 * BN : BN;
+    if (warp == 8) tmem_alloc(tmem_slot, kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -315,9 +235,9 @@ gemm_tc_kernel(ALoad A, BLoad B, Epi epi, int num_kb_total, int kb_per_split) {
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k) {     // +32 bytes (>>4 = 2) per K=8 step inside the swizzle row
                 if (WITH_LO) {
-                    umma_tf32(tmem_base, a_lo + 2 * k, b_hi + 2 * k, idesc, (i | k) != 0);
-                    umma_tf32(tmem_base, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
-                    umma_tf32(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);
+                    umma_tf32(tmem_base + BN, a_lo + 2 * k, b_hi + 2 * k, idesc, (i | k) != 0);
+                    umma_tf32(tmem_base + BN, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+                    umma_tf32(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, (i | k) != 0);
                 } else {
                     umma_tf32(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, (i | k) != 0);
                 }
@@ -341,6 +261,12 @@ gemm_tc_kernel(ALoad A, BLoad B, Epi epi, int num_kb_total, int kb_per_split) {
             uint32_t r[16];
             if (nkb > 0) {
                 tmem_ld16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)col, r);
+                if (WITH_LO) {
+                    uint32_t r2[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(BN + col), r2);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) r[j] = 0u;
@@ -350,7 +276,7 @@ gemm_tc_kernel(ALoad A, BLoad B, Epi epi, int num_kb_total, int kb_per_split) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, BN);
+    if (warp == 8) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ---------------------------------------------------------------------------------------------- helper kernels
@@ -410,6 +336,21 @@ static inline int ew_blocks(int64_t n) {
 // ------------------------------------------------------------------------------------------------ entry points
 // (called from clb_gemm_simt.cu's C-ABI functions when the matmul mode selects tensor cores and the shape qualifies)
 
+int tc2_conv_fwd(const float* x, const float* w2, const float* bias, float* y, int N, int C, int H, int W, int K, int R,
+                 int S, int pad, int relu, bool with_lo, cudaStream_t s);
+int tc2_conv_wgrad(const float* x, const float* dy, float* ws, int N, int C, int H, int W, int K, int R, int S, int pad,
+                   bool with_lo, cudaStream_t s);
+
+// CLB_TC_IMPL=1 selects the first-generation kernel (both operands through smem); default 2 (A through TMEM)
+static int tc_impl() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("CLB_TC_IMPL");
+        v = (e && e[0] == '1') ? 1 : 2;
+    }
+    return v;
+}
+
 bool tc_conv_supported(int C, int H, int W, int K, int R, int S, int stride, int pad) {
     const int P = H + 2 * pad - R + 1, Q = W + 2 * pad - S + 1;
     return stride == 1 && R == S && (C % 32) == 0 && (K % 32) == 0 && P == H && Q == W && (Q % 4) == 0 && R * S <= 25;
@@ -420,6 +361,7 @@ size_t tc_weight_ws_floats(int C, int K, int R, int S) { return (size_t)K * C * 
 int tc_conv_fwd(const float* x, const float* w2 /*[K][RS][C]*/, const float* bias, float* y, int N, int C, int H, int W,
                 int K, int R, int S, int pad, int relu, bool with_lo, cudaStream_t s) {
     using namespace tc;
+    if (tc_impl() == 2) return tc2_conv_fwd(x, w2, bias, y, N, C, H, W, K, R, S, pad, relu, with_lo, s);
     const int P = H, Q = W, M = N * P * Q;
     PixelGather A{x, C, H, W, R, S, pad, P, Q, M, FastDiv32(P * Q), FastDiv32(Q), FastDiv32(C), FastDiv32(S)};
     EpiNCHW e{y, bias, relu, M, K, P * Q, FastDiv32(P * Q)};
@@ -465,7 +407,9 @@ int tc_conv_wgrad(const float* x, const float* dy, float* dw, float* ws, int N, 
     RowsKContig<128> A{dy, K, (int64_t)P * Q, npix, P * Q, (int64_t)K * P * Q, FastDiv32(P * Q)};
     EpiSplitK e{ws, K, n_rows, (int64_t)K * n_rows};
     int rc;
-    if (bn == 128) {
+    if (tc_impl() == 2) {
+        rc = tc2_conv_wgrad(x, dy, ws, N, C, H, W, K, R, S, pad, with_lo, s);
+    } else if (bn == 128) {
         TapRowsOverPixels<128> B{x, C, H, W, R, S, pad, P, Q, n_rows, npix, FastDiv32(P * Q), FastDiv32(Q), FastDiv32(C), FastDiv32(S)};
         dim3 grid((K + BM - 1) / BM, (n_rows + 127) / 128, splits);
         rc = with_lo ? launch<128, 3, true>(A, B, e, grid, nkb, per, s) : launch<128, 4, false>(A, B, e, grid, nkb, per, s);

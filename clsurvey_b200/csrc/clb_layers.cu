@@ -81,6 +81,55 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* 
     }
 }
 
+// 2x2 / stride-2 specialisation (every VGG pool): one thread per PAIR of adjacent outputs -> float4 input rows,
+// float2 output; H, W even and W % 4 == 0.  Same first-max-wins rule.
+__global__ void maxpool2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ am,
+                                    int64_t total_pairs, int H, int W) {
+    const int PW2 = W >> 2, PH = H >> 1;
+    const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total_pairs; t += gs) {
+        const int pw2 = (int)(t % PW2), ph = (int)((t / PW2) % PH);
+        const int64_t nc = t / ((int64_t)PW2 * PH);
+        const float* src = x + nc * H * W + (int64_t)(2 * ph) * W + 4 * pw2;
+        const float4 r0 = *reinterpret_cast<const float4*>(src), r1 = *reinterpret_cast<const float4*>(src + W);
+        float b0 = r0.x; int i0 = 0;
+        if (r0.y > b0 || r0.y != r0.y) { b0 = r0.y; i0 = 1; }
+        if (r1.x > b0 || r1.x != r1.x) { b0 = r1.x; i0 = 2; }
+        if (r1.y > b0 || r1.y != r1.y) { b0 = r1.y; i0 = 3; }
+        float b1 = r0.z; int i1 = 0;
+        if (r0.w > b1 || r0.w != r0.w) { b1 = r0.w; i1 = 1; }
+        if (r1.z > b1 || r1.z != r1.z) { b1 = r1.z; i1 = 2; }
+        if (r1.w > b1 || r1.w != r1.w) { b1 = r1.w; i1 = 3; }
+        const int64_t o = (nc * PH + ph) * (W >> 1) + 2 * pw2;
+        *reinterpret_cast<float2*>(y + o) = make_float2(b0, b1);
+        *reinterpret_cast<uchar2*>(am + o) = make_uchar2((unsigned char)i0, (unsigned char)i1);
+    }
+}
+__global__ void maxpool2_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ am,
+                                    const float* __restrict__ relu_out, float* __restrict__ dx, int64_t total_pairs,
+                                    int H, int W) {
+    const int PW2 = W >> 2, PH = H >> 1;
+    const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total_pairs; t += gs) {
+        const int pw2 = (int)(t % PW2), ph = (int)((t / PW2) % PH);
+        const int64_t nc = t / ((int64_t)PW2 * PH);
+        const int64_t o = (nc * PH + ph) * (W >> 1) + 2 * pw2;
+        const float2 d = *reinterpret_cast<const float2*>(dy + o);
+        const uchar2 a = *reinterpret_cast<const uchar2*>(am + o);
+        const int64_t ioff = nc * H * W + (int64_t)(2 * ph) * W + 4 * pw2;
+        float4 r0 = make_float4(a.x == 0 ? d.x : 0.f, a.x == 1 ? d.x : 0.f, a.y == 0 ? d.y : 0.f, a.y == 1 ? d.y : 0.f);
+        float4 r1 = make_float4(a.x == 2 ? d.x : 0.f, a.x == 3 ? d.x : 0.f, a.y == 2 ? d.y : 0.f, a.y == 3 ? d.y : 0.f);
+        if (relu_out) {
+            const float4 m0 = *reinterpret_cast<const float4*>(relu_out + ioff);
+            const float4 m1 = *reinterpret_cast<const float4*>(relu_out + ioff + W);
+            r0.x = m0.x > 0.f ? r0.x : 0.f; r0.y = m0.y > 0.f ? r0.y : 0.f; r0.z = m0.z > 0.f ? r0.z : 0.f; r0.w = m0.w > 0.f ? r0.w : 0.f;
+            r1.x = m1.x > 0.f ? r1.x : 0.f; r1.y = m1.y > 0.f ? r1.y : 0.f; r1.z = m1.z > 0.f ? r1.z : 0.f; r1.w = m1.w > 0.f ? r1.w : 0.f;
+        }
+        *reinterpret_cast<float4*>(dx + ioff) = r0;
+        *reinterpret_cast<float4*>(dx + ioff + W) = r1;
+    }
+}
+
 // AdaptiveAvgPool2d: window of output (oh,ow) = [floor(oh*H/OH), ceil((oh+1)*H/OH))
 __global__ void aavgpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t total, int H, int W,
                                     int OH, int OW) {
@@ -209,6 +258,12 @@ int clb_maxpool_fwd(const float* x, float* y, uint8_t* argmax, int N, int C, int
     CLB_CHECK_ARG(x && y && argmax && N > 0 && C > 0 && k >= 1 && k <= 15 && stride >= 1 && H >= k && W >= k);
     const int PH = (H - k) / stride + 1, PW = (W - k) / stride + 1;
     const int64_t total = (int64_t)N * C * PH * PW;
+    if (k == 2 && stride == 2 && (W & 3) == 0 && (H & 1) == 0 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0) {
+        const int64_t pairs = total >> 1;
+        maxpool2_fwd_kernel<<<ew_grid(pairs, 256), 256, 0, as_stream(stream)>>>(x, y, argmax, pairs, H, W); clb::count_launch();
+        CLB_CHECK_LAUNCH();
+        return CLB_OK;
+    }
     maxpool_fwd_kernel<<<ew_grid(total, 256), 256, 0, as_stream(stream)>>>(x, y, argmax, total, H, W, PH, PW, k, stride); clb::count_launch();
     CLB_CHECK_LAUNCH();
     return CLB_OK;
@@ -219,6 +274,12 @@ int clb_maxpool_bwd(const float* dy, const uint8_t* argmax, const float* x_relu_
     CLB_CHECK_ARG(dy && argmax && dx && N > 0 && C > 0 && k >= 1 && k <= 15 && stride >= 1 && H >= k && W >= k);
     const int PH = (H - k) / stride + 1, PW = (W - k) / stride + 1;
     const int64_t total = (int64_t)N * C * H * W;
+    if (k == 2 && stride == 2 && (W & 3) == 0 && (H & 1) == 0 && (((uintptr_t)dy | (uintptr_t)dx | (uintptr_t)x_relu_out) & 15) == 0) {
+        const int64_t pairs = total >> 3;
+        maxpool2_bwd_kernel<<<ew_grid(pairs, 256), 256, 0, as_stream(stream)>>>(dy, argmax, x_relu_out, dx, pairs, H, W); clb::count_launch();
+        CLB_CHECK_LAUNCH();
+        return CLB_OK;
+    }
     maxpool_bwd_kernel<<<ew_grid(total, 256), 256, 0, as_stream(stream)>>>(dy, argmax, x_relu_out, dx, total, H, W, PH,
                                                                             PW, k, stride); clb::count_launch();
     CLB_CHECK_LAUNCH();

@@ -127,6 +127,7 @@ class Engine:
                 p.grad = self.grad[o:o + p.numel()].view(p.shape)
                 _ENGINES[id(p)] = self
         del old_theta
+        self._graphs = {}
         self._compile()
 
     def view(self, flat, i):
@@ -379,6 +380,35 @@ class Engine:
     def fwd_loss(self, x, y, mode=LOSS_MEAN_CE, col_off=0, ncols=None):
         self.forward(x, train=False)
         self.loss_head(y, mode, None, col_off, ncols, want_grad=False)
+
+    # ------------------------------------------------------------------ CUDA-graph replay of a whole step
+    def graphed(self, key, n, body):
+        """Capture `body(x_static, y_static)` (a sequence of C-ABI launches on the current stream) once per `key` and
+        return a callable(x, y) that copies the batch into the static buffers and replays the graph.  Capturing does
+        not execute anything, so the caller must have run `body` eagerly at least once before (lazy kernel attributes,
+        momentum buffers).  Turns the ~75 launches + ctypes calls of a VGG-11 step into one graph launch."""
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        ent = self._graphs.get(key)
+        if ent is None:
+            xs = torch.empty((n,) + self.input_shape, dtype=torch.float32, device=self.device)
+            ys = torch.zeros(n, dtype=torch.int64, device=self.device)
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                body(xs, ys)
+            ent = (g, xs, ys)
+            self._graphs[key] = ent
+        g, xs, ys = ent
+
+        def run(x, y):
+            xs.copy_(x, non_blocking=True)
+            ys.copy_(y, non_blocking=True)
+            g.replay()
+        return run
+
+    def drop_graphs(self):
+        self._graphs = {}
 
     def read_loss_correct(self):
         """One device->host read of (loss, #correct) -- the reference does this every batch (train_EWC.py:196-197)."""

@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libclb.so")
+LIB_PATH = os.environ.get("CLB_LIB_PATH") or os.path.join(_HERE, "_lib", "libclb.so")   # CLB_LIB_PATH: A/B builds
 
 _lib = None
 

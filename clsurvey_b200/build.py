@@ -42,8 +42,11 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, extra_flags=(), out_name=None):
+    """extra_flags / out_name: experimental variants (e.g. -DCLB_TC2_GROUPS=4 -> libclb_g4.so, loaded via CLB_LIB_PATH)."""
     os.makedirs(OUT_DIR, exist_ok=True)
+    if out_name:
+        return _build_variant(list(extra_flags), out_name)
     stamp = os.path.join(OUT_DIR, "build.stamp")
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
@@ -69,6 +72,24 @@ def build(force=False, verbose=False):
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
     open(stamp, "w").write(dig)
     return LIB
+
+
+def _build_variant(extra, out_name):
+    nvcc = _nvcc()
+    vdir = os.path.join(OUT_DIR, "variant_" + out_name)
+    os.makedirs(vdir, exist_ok=True)
+    objs = []
+    for src in sources():
+        obj = os.path.join(vdir, os.path.basename(src)[:-3] + ".o")
+        r = subprocess.run([nvcc] + ARCH + FLAGS + extra + ["-c", src, "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(r.stderr)
+        objs.append(obj)
+    lib = os.path.join(OUT_DIR, out_name)
+    r = subprocess.run([nvcc] + ARCH + ["-shared", "-o", lib] + objs + ["-ldl"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(r.stderr)
+    return lib
 
 
 if __name__ == "__main__":

@@ -55,7 +55,9 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 
 // tensor-core (tcgen05) path, clb_gemm_tc.cu
-bool tc_conv_supported(int C, int H, int W, int K, int R, int S, int stride, int pad);
+bool tc_fwd_supported(int C, int H, int W, int K, int R, int S, int stride, int pad);
+bool tc_dgrad_supported(int C, int H, int W, int K, int R, int S, int stride, int pad);
+bool tc_wgrad_supported(int C, int H, int W, int K, int R, int S, int stride, int pad);
 int tc_conv_fwd(const float* x, const float* w2, const float* bias, float* y, int N, int C, int H, int W, int K, int R,
                 int S, int pad, int relu, bool with_lo, cudaStream_t s);
 size_t tc_wgrad_ws_floats(int N, int C, int H, int W, int K, int R, int S);

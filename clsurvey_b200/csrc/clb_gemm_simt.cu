@@ -444,7 +444,7 @@ int clb_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, 
     CLB_CHECK_ARG(H + 2 * pad >= R && W + 2 * pad >= S);
     CLB_CHECK_ARG((int64_t)N * C * H * W < (1LL << 31) && (int64_t)N * K * H * W < (1LL << 31));
     ConvGeom g = make_geom(N, C, H, W, K, R, S, stride, pad);
-    if (mm_mode() != CLB_MM_FP32_SIMT && w_ws != nullptr && tc_conv_supported(C, H, W, K, R, S, stride, pad)) {
+    if (mm_mode() != CLB_MM_FP32_SIMT && w_ws != nullptr && tc_fwd_supported(C, H, W, K, R, S, stride, pad)) {
         tc_permute_w_fwd(w, w_ws, K, C, R * S, as_stream(stream));           // [K][C][RS] -> [K][RS][C]
         int rc = tc_conv_fwd(x, w_ws, bias, y, N, C, H, W, K, R, S, pad, relu, mm_mode() == CLB_MM_TF32X3, as_stream(stream));
         if (rc) return rc;
@@ -461,8 +461,7 @@ int clb_conv2d_dgrad(const float* dy, const float* w, float* dx, float* wt_ws, i
     CLB_CHECK_ARG(dy && w && dx && N > 0 && C > 0 && H > 0 && W > 0 && K > 0 && R > 0 && S > 0 && stride > 0 && pad >= 0);
     cudaStream_t s = as_stream(stream);
     ConvGeom g = make_geom(N, C, H, W, K, R, S, stride, pad);
-    if (mm_mode() != CLB_MM_FP32_SIMT && wt_ws != nullptr && R - 1 - pad >= 0 &&
-        tc_conv_supported(C, H, W, K, R, S, stride, pad) && tc_conv_supported(K, g.P, g.Q, C, R, S, 1, R - 1 - pad)) {
+    if (mm_mode() != CLB_MM_FP32_SIMT && wt_ws != nullptr && tc_dgrad_supported(C, H, W, K, R, S, stride, pad)) {
         tc_permute_w_dgrad(w, wt_ws, K, C, R, S, s);                          // [K][C][R][S] -> [C][flipped RS][K]
         int rc = tc_conv_fwd(dy, wt_ws, nullptr, dx, N, K, g.P, g.Q, C, R, S, R - 1 - pad, 0, mm_mode() == CLB_MM_TF32X3, s);
         if (rc) return rc;
@@ -494,7 +493,7 @@ size_t clb_conv2d_wgrad_ws(int N, int C, int H, int W, int K, int R, int S, int 
     int splits, chunk, bm;
     wgrad_plan(g, &splits, &chunk, &bm);
     size_t need = (size_t)splits * K * C * R * S * sizeof(float);
-    if (tc_conv_supported(C, H, W, K, R, S, stride, pad)) {
+    if (tc_wgrad_supported(C, H, W, K, R, S, stride, pad)) {
         const size_t t = tc_wgrad_ws_floats(N, C, H, W, K, R, S) * sizeof(float);
         if (t > need) need = t;
     }
@@ -508,7 +507,7 @@ int clb_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias, f
     cudaStream_t s = as_stream(stream);
     ConvGeom g = make_geom(N, C, H, W, K, R, S, stride, pad);
     const int M = K, Ng = C * R * S, Kg = N * g.P * g.Q;
-    if (mm_mode() != CLB_MM_FP32_SIMT && tc_conv_supported(C, H, W, K, R, S, stride, pad)) {
+    if (mm_mode() != CLB_MM_FP32_SIMT && tc_wgrad_supported(C, H, W, K, R, S, stride, pad)) {
         const size_t tneed = tc_wgrad_ws_floats(N, C, H, W, K, R, S) * sizeof(float);
         if (ws == nullptr || ws_bytes < tneed) {
             set_error("clb_conv2d_wgrad: workspace %zu bytes < required %zu", ws_bytes, tneed);

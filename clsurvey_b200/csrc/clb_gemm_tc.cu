@@ -150,7 +150,7 @@ struct EpiSplitK {   // ws[z][m][n] row-major partial sums (wgrad); reduced in f
     __device__ __forceinline__ void store16(int m, int n0, const uint32_t (&r)[16], int z) const {
         if (m >= M) return;
         float* dst = ws + (int64_t)z * split_stride + (int64_t)m * N + n0;
-        if (n0 + 15 < N) {
+        if (n0 + 15 < N && (N & 3) == 0) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
                 *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
@@ -280,12 +280,13 @@ gemm_tc_kernel(ALoad A, BLoad B, Epi epi, int num_kb_total, int kb_per_split) {
 }
 
 // ---------------------------------------------------------------------------------------------- helper kernels
-// w[K][C][RS] -> w2[K][RS][C]   (forward GEMM-B, K order (r,s,c))
-__global__ void permute_w_fwd_kernel(const float* __restrict__ w, float* __restrict__ w2, int K, int C, int RS) {
-    const int64_t total = (int64_t)K * C * RS, gs = (int64_t)gridDim.x * blockDim.x;
+// w[K][C][RS] -> w2[K][ld] with w2[k][rs*C + c]   (forward GEMM-B, K order (r,s,c)); ld > RS*C zero-pads the row
+__global__ void permute_w_fwd_kernel(const float* __restrict__ w, float* __restrict__ w2, int K, int C, int RS, int ld) {
+    const int64_t total = (int64_t)K * ld, gs = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gs) {
-        const int c = (int)(i % C), rs = (int)((i / C) % RS), k = (int)(i / ((int64_t)C * RS));
-        w2[i] = w[((int64_t)k * C + c) * RS + rs];
+        const int j = (int)(i % ld), k = (int)(i / ld);
+        const int c = j % C, rs = j / C;
+        w2[i] = (j < RS * C) ? w[((int64_t)k * C + c) * RS + rs] : 0.f;
     }
 }
 // w[K][C][R][S] -> wd[C][(R-1-r, S-1-s)][K]   (dgrad = forward conv of dY: rows = c, K order (r', s', kout))
@@ -351,9 +352,23 @@ static int tc_impl() {
     return v;
 }
 
-bool tc_conv_supported(int C, int H, int W, int K, int R, int S, int stride, int pad) {
-    const int P = H + 2 * pad - R + 1, Q = W + 2 * pad - S + 1;
-    return stride == 1 && R == S && (C % 32) == 0 && (K % 32) == 0 && P == H && Q == W && (Q % 4) == 0 && R * S <= 25;
+// shapes the tensor-core path takes (everything else stays on the exact-fp32 SIMT kernels):
+//   fwd  : stride 1, "same" padding, C % 32 == 0 (one filter tap per K block) or the whole C*R*S <= 32 (first layer; gen-2 only)
+//   dgrad: a forward conv of dY, i.e. the fwd rule with C := K
+//   wgrad: stride 1, "same" padding, Q % 4 == 0 (16-byte pixel chunks)
+static bool same_conv(int H, int W, int R, int S, int stride, int pad) {
+    return stride == 1 && R == S && 2 * pad == R - 1 && H > 0 && W > 0;
+}
+bool tc_fwd_supported(int C, int H, int W, int K, int R, int S, int stride, int pad) {
+    if (!same_conv(H, W, R, S, stride, pad)) return false;
+    return (C % 32) == 0 || (tc_impl() == 2 && C * R * S <= 32);
+}
+bool tc_dgrad_supported(int C, int H, int W, int K, int R, int S, int stride, int pad) {
+    return same_conv(H, W, R, S, stride, pad) && (K % 32) == 0;
+}
+bool tc_wgrad_supported(int C, int H, int W, int K, int R, int S, int stride, int pad) {
+    if (!same_conv(H, W, R, S, stride, pad) || (W % 4) != 0) return false;
+    return tc_impl() == 2 || (C % 32) == 0;
 }
 
 size_t tc_weight_ws_floats(int C, int K, int R, int S) { return (size_t)K * C * R * S; }
@@ -424,7 +439,8 @@ int tc_conv_wgrad(const float* x, const float* dy, float* dw, float* ws, int N, 
 }
 
 void tc_permute_w_fwd(const float* w, float* w2, int K, int C, int RS, cudaStream_t s) {
-    tc::permute_w_fwd_kernel<<<tc::ew_blocks((int64_t)K * C * RS), 256, 0, s>>>(w, w2, K, C, RS); clb::count_launch();
+    const int ld = (C % 32 == 0) ? RS * C : 32;
+    tc::permute_w_fwd_kernel<<<tc::ew_blocks((int64_t)K * ld), 256, 0, s>>>(w, w2, K, C, RS, ld); clb::count_launch();
 }
 void tc_permute_w_dgrad(const float* w, float* wd, int K, int C, int R, int S, cudaStream_t s) {
     tc::permute_w_dgrad_kernel<<<tc::ew_blocks((int64_t)K * C * R * S), 256, 0, s>>>(w, wd, K, C, R, S); clb::count_launch();

@@ -8,17 +8,29 @@
 //   * only B (BN x 32, hi / lo) is staged in swizzled smem: 32 KB written + 48 KB read per K block = 640 clk < 768 clk;
 //   * loaders issue their global loads BEFORE waiting for a free stage, two A groups alternate K blocks, and the B
 //     loader warp group prefetches one K block ahead.
-// Warp roles (416 threads): warps 0-3 / 4-7 = A loader groups (warp%4 = TMEM lane quarter), warps 8-11 = B loaders,
-// warp 12 = TMEM allocator + MMA issuer; warps 0-7 run the epilogue.
-// TMEM columns: [0,BN) hi*hi accumulator, [BN,2BN) cross-term accumulator, then 3 A stages x (32 hi + 32 lo) columns.
+// Warp roles (default 544 threads): 2 A loader groups (warps 0-7, warp%4 = TMEM lane quarter), 2 B loader groups (warps
+// 8-15), warp 16 = TMEM allocator + MMA issuer; warps 0-7 run the epilogue.  Group counts are compile-time (-DCLB_TC2_GROUPS*).
+// TMEM columns: [0,BN) hi*hi accumulator, [BN,2BN) cross-term accumulator, then 4 A stages x (32 hi + 32 lo) columns = 512.
+#include <limits.h>
+
 #include "clb_tc_ptx.cuh"
 
 namespace clb {
 namespace tc2 {
 using namespace clb::tc;
 
-constexpr int kThreads = 416;
-constexpr int kStagesA = 3;
+#ifndef CLB_TC2_GROUPS
+#define CLB_TC2_GROUPS 2
+#endif
+constexpr int kGroupsA = CLB_TC2_GROUPS;                   // A loader groups (4 warps each); K block i belongs to group i % kGroupsA
+#ifndef CLB_TC2_GROUPS_B
+#define CLB_TC2_GROUPS_B 2
+#endif
+constexpr int kGroupsB = CLB_TC2_GROUPS_B;                   // B loader groups (4 warps each); K block i belongs to group i % kGroupsB
+constexpr int kWarpsA = 4 * kGroupsA;
+constexpr int kWarpMma = kWarpsA + 4 * kGroupsB;             // first warp after the loaders issues the MMAs
+constexpr int kThreads = (kWarpMma + 1) * 32;                // default 2+2 groups: 17 warps = 544 threads (<= 96 regs)
+constexpr int kStagesA = 4;                                  // TMEM A stages (4 x 64 columns + 256 accumulator columns = 512)
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
@@ -48,33 +60,73 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
 struct PixelRows {          // conv fwd / dgrad: row = output pixel, K = (r, s, c) over an NCHW tensor, stride 1
     const float* x; int C, H, W, R, S, pad, P, Q, M;
     FastDiv32 dPQ, dQ, dC, dS;
-    __device__ __forceinline__ void row(int kb, int m, float (&v)[BK]) const {
-        const uint32_t k0 = (uint32_t)kb * BK;
-        const uint32_t rs = dC.div(k0), c0 = k0 - rs * C;
-        const uint32_t r = dS.div(rs), s = rs - r * S;
+    struct Ctx { const float* pix; int p, q; bool ok; };          // per-thread, constant over the K loop
+    __device__ __forceinline__ Ctx prep(int m) const {
         const uint32_t img = dPQ.div(m), pq = m - img * (P * Q);
         const uint32_t p = dQ.div(pq), q = pq - p * Q;
-        const int ih = (int)p + (int)r - pad, iw = (int)q + (int)s - pad;
-        const bool ok = m < M && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W;
-        const float* src = x + ((size_t)img * C + c0) * H * W + (ok ? ih * W + iw : 0);
+        return {x + (size_t)img * C * H * W + (int)p * W + (int)q, (int)p, (int)q, m < M};
+    }
+    __device__ __forceinline__ void row(int kb, const Ctx& t, float (&v)[BK]) const {
+        const uint32_t k0 = (uint32_t)kb * BK;                     // warp-uniform tap decomposition
+        const uint32_t rs = dC.div(k0), c0 = k0 - rs * C;
+        const uint32_t r = dS.div(rs), s = rs - r * S;
+        const int dr = (int)r - pad, ds = (int)s - pad;
+        const bool ok = t.ok && (unsigned)(t.p + dr) < (unsigned)H && (unsigned)(t.q + ds) < (unsigned)W;
         const int HW = H * W;
+        const float* src = t.pix + ((int)c0 * HW + dr * W + ds);
 #pragma unroll
-        for (int j = 0; j < BK; ++j) v[j] = ok ? __ldg(src + (size_t)j * HW) : 0.f;
+        for (int j = 0; j < BK; ++j) v[j] = ok ? __ldg(src + j * HW) : 0.f;
+    }
+};
+
+struct PixelRowsSmallC {    // first layer (C*R*S <= 32, e.g. 3x3x3 = 27): the whole reduction is ONE zero-padded K block
+    const float* x; int C, H, W, R, S, pad, P, Q, M, ktot;
+    FastDiv32 dPQ, dQ, dC, dS;
+    struct Ctx { int m; };
+    __device__ __forceinline__ Ctx prep(int m) const { return {m}; }
+    __device__ __forceinline__ void row(int /*kb*/, const Ctx& t, float (&v)[BK]) const {
+        const int m = t.m;
+        const uint32_t img = dPQ.div(m), pq = m - img * (P * Q);
+        const uint32_t p = dQ.div(pq), q = pq - p * Q;
+        const float* base = x + (size_t)img * C * H * W;
+        const bool mok = m < M;
+#pragma unroll
+        for (int j = 0; j < BK; ++j) {
+            const uint32_t rs = dC.div(j), c = j - rs * C;
+            const uint32_t r = dS.div(rs), s = rs - r * S;
+            const int ih = (int)p + (int)r - pad, iw = (int)q + (int)s - pad;
+            const bool ok = mok && j < ktot && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W;
+            v[j] = ok ? __ldg(base + ((size_t)c * H + ih) * W + iw) : 0.f;
+        }
     }
 };
 
 struct DyRows {             // conv wgrad: row = output channel kout, K = pixel: dy[img][kout][pq], 16-byte chunks
     const float* dy; int K, PQ, npix; FastDiv32 dPQ;
-    __device__ __forceinline__ void row(int kb, int m, float (&v)[BK]) const {
-        const bool rok = m < K;
+    struct Ctx { const float* rowp; bool ok; };
+    __device__ __forceinline__ Ctx prep(int m) const { return {dy + (size_t)m * PQ, m < K}; }
+    __device__ __forceinline__ void row(int kb, const Ctx& t, float (&v)[BK]) const {
+        const size_t img_stride = (size_t)K * PQ;
+        if ((PQ & 31) == 0) {                                      // the whole K block lies in one image (uniform)
+            const int pix0 = kb * BK;
+            const uint32_t img = dPQ.div(pix0), pq0 = pix0 - img * PQ;
+            const bool ok = t.ok && pix0 < npix;
+            const float4* src = reinterpret_cast<const float4*>(t.rowp + img * img_stride + pq0);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const int pix = kb * BK + c * 4;
-            const uint32_t img = dPQ.div(pix), pq = pix - img * PQ;
-            const bool ok = rok && pix < npix;
-            const float4 t = ok ? __ldg(reinterpret_cast<const float4*>(dy + ((size_t)img * K + m) * PQ + pq))
-                                : make_float4(0, 0, 0, 0);
-            v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+            for (int c = 0; c < 8; ++c) {
+                const float4 q = ok ? __ldg(src + c) : make_float4(0, 0, 0, 0);
+                v[4 * c] = q.x; v[4 * c + 1] = q.y; v[4 * c + 2] = q.z; v[4 * c + 3] = q.w;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int pix = kb * BK + c * 4;
+                const uint32_t img = dPQ.div(pix), pq = pix - img * PQ;
+                const bool ok = t.ok && pix < npix;
+                const float4 q = ok ? __ldg(reinterpret_cast<const float4*>(t.rowp + img * img_stride + pq))
+                                    : make_float4(0, 0, 0, 0);
+                v[4 * c] = q.x; v[4 * c + 1] = q.y; v[4 * c + 2] = q.z; v[4 * c + 3] = q.w;
+            }
         }
     }
 };
@@ -85,14 +137,22 @@ template <int ROWS> struct BRegs { float4 v[ROWS / 16]; };
 template <int ROWS>
 struct WeightRows {         // rows contiguous along K: w2[rows][ld]
     const float* p; int n_rows; int64_t ld; int k_total;
-    __device__ __forceinline__ void load(int kb, int tg, int row0, BRegs<ROWS>& g) const {
-        const int kk = kb * BK + (tg & 7) * 4;
-        const bool kok = kk < k_total;
+    struct Ctx { const float* rp[ROWS / 16]; };                   // per-thread row pointers (+ chunk offset), NULL = masked
+    __device__ __forceinline__ Ctx prep(int tg, int row0) const {
+        Ctx t;
 #pragma unroll
         for (int i = 0; i < ROWS / 16; ++i) {
             const int r = row0 + (tg >> 3) + 16 * i;
-            g.v[i] = (kok && r < n_rows) ? __ldg(reinterpret_cast<const float4*>(p + (int64_t)r * ld + kk)) : make_float4(0, 0, 0, 0);
+            t.rp[i] = r < n_rows ? p + (int64_t)r * ld + (tg & 7) * 4 : nullptr;
         }
+        return t;
+    }
+    __device__ __forceinline__ void load(int kb, int tg, const Ctx& t, BRegs<ROWS>& g) const {
+        const int kk = kb * BK;
+        const bool kok = kk + (tg & 7) * 4 < k_total;
+#pragma unroll
+        for (int i = 0; i < ROWS / 16; ++i)
+            g.v[i] = (kok && t.rp[i]) ? __ldg(reinterpret_cast<const float4*>(t.rp[i] + kk)) : make_float4(0, 0, 0, 0);
     }
 };
 
@@ -100,27 +160,35 @@ template <int ROWS>
 struct TapRows {            // conv wgrad B: row = (r, s, c) tap, K = pixel (4 consecutive pixels of an image row per chunk)
     const float* x; int C, H, W, R, S, pad, P, Q, n_rows, k_total;
     FastDiv32 dPQ, dQ, dC, dS;
-    __device__ __forceinline__ void load(int kb, int tg, int row0, BRegs<ROWS>& g) const {
-        const int pix = kb * BK + (tg & 7) * 4;
-        const uint32_t img = dPQ.div(pix), pq = pix - img * (P * Q);
-        const uint32_t p = dQ.div(pq), q0 = pq - p * Q;
-        const bool kok = pix < k_total;
-        const float* img_base = x + (size_t)img * C * H * W;
+    struct Ctx { int off[ROWS / 16]; short dr[ROWS / 16], ds[ROWS / 16]; };   // off = c*H*W + dr*W + ds, or -1 = masked row
+    __device__ __forceinline__ Ctx prep(int tg, int row0) const {
+        Ctx t;
 #pragma unroll
         for (int i = 0; i < ROWS / 16; ++i) {
             const int n = row0 + (tg >> 3) + 16 * i;
             const uint32_t rs = dC.div(n), c = n - rs * C;
             const uint32_t r = dS.div(rs), s = rs - r * S;
-            const int ih = (int)p + (int)r - pad, iw0 = (int)q0 + (int)s - pad;
-            const bool rok = kok && n < n_rows && (unsigned)ih < (unsigned)H;
-            const float* src = img_base + ((size_t)c * H + (rok ? ih : 0)) * W;
-            float t[4];
+            t.dr[i] = (short)((int)r - pad);
+            t.ds[i] = (short)((int)s - pad);
+            t.off[i] = n < n_rows ? (int)c * H * W + t.dr[i] * W + t.ds[i] : INT_MIN;
+        }
+        return t;
+    }
+    __device__ __forceinline__ void load(int kb, int tg, const Ctx& t, BRegs<ROWS>& g) const {
+        const int pix = kb * BK + (tg & 7) * 4;
+        const uint32_t img = dPQ.div(pix), pq = pix - img * (P * Q);
+        const uint32_t p = dQ.div(pq), q0 = pq - p * Q;
+        const bool kok = pix < k_total;
+        const float* base = x + (size_t)img * C * H * W + (int)p * W + (int)q0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int iw = iw0 + j;
-                t[j] = (rok && (unsigned)iw < (unsigned)W) ? __ldg(src + iw) : 0.f;
-            }
-            g.v[i] = make_float4(t[0], t[1], t[2], t[3]);
+        for (int i = 0; i < ROWS / 16; ++i) {
+            const int ih = (int)p + t.dr[i], iw0 = (int)q0 + t.ds[i];
+            const bool rok = kok && t.off[i] != INT_MIN && (unsigned)ih < (unsigned)H;
+            const float* src = base + (rok ? t.off[i] : 0);
+            float u[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) u[j] = (rok && (unsigned)(iw0 + j) < (unsigned)W) ? __ldg(src + j) : 0.f;
+            g.v[i] = make_float4(u[0], u[1], u[2], u[3]);
         }
     }
 };
@@ -128,10 +196,11 @@ struct TapRows {            // conv wgrad B: row = (r, s, c) tap, K = pixel (4 c
 template <int ROWS, bool WITH_LO>
 __device__ __forceinline__ void store_b(const BRegs<ROWS>& g, int tg, uint32_t tile_hi, uint32_t tile_lo) {
     const int c = tg & 7;
+    const int r0 = tg >> 3;                       // rows r0 + 16 i: (r & 7) == (r0 & 7) for every i -> one swizzled offset
+    const uint32_t off0 = (uint32_t)r0 * 128u + (uint32_t)((c ^ (r0 & 7)) << 4);
 #pragma unroll
     for (int i = 0; i < ROWS / 16; ++i) {
-        const int r = (tg >> 3) + 16 * i;
-        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+        const uint32_t off = off0 + (uint32_t)i * 2048u;
         const float4 v = g.v[i];
         const uint32_t h0 = __float_as_uint(v.x) & kHiMask, h1 = __float_as_uint(v.y) & kHiMask;
         const uint32_t h2 = __float_as_uint(v.z) & kHiMask, h3 = __float_as_uint(v.w) & kHiMask;
@@ -162,7 +231,7 @@ struct EpiSplitK {
     __device__ __forceinline__ void store16(int m, int n0, const uint32_t (&r)[16], int z) const {
         if (m >= M) return;
         float* dst = ws + (int64_t)z * split_stride + (int64_t)m * N + n0;
-        if (n0 + 15 < N) {
+        if (n0 + 15 < N && (N & 3) == 0) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
                 *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
@@ -211,20 +280,23 @@ gemm_tc2_kernel(ALoad A, BLoad B, Epi epi, int num_kb_total, int kb_per_split) {
         mbar_init(bar_tmem, 1);
         fence_barrier_init();
     }
-    if (warp == 12) tmem_alloc(tmem_slot, L::kTmemCols);
+    if (warp == kWarpMma) tmem_alloc(tmem_slot, L::kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     const uint32_t tmem_a0 = tmem_base + L::kAccCols;
 
-    if (warp < 8) {
-        // ---------------- A loaders: registers -> TMEM; group g owns K blocks with i % 2 == g; thread = one GEMM row
+    if (warp < kWarpsA) {
+        // ---------------- A loaders: registers -> TMEM; group g owns K blocks with i % kGroupsA == g; thread = one GEMM row.
+        // ncu (r1_ncu_full_gemm_tc_v1): with 2 groups the loader warps ran at ~0.25 IPC on dependent address math and
+        // LDG latency (~3300 clk per group per K block vs 768 clk of MMA): more groups in flight, not more bandwidth.
         const int group = warp >> 2, tg = threadIdx.x & 127;
         const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
-        for (int i = group; i < nkb; i += 2) {
+        const typename ALoad::Ctx actx = A.prep(m0 + tg);
+        for (int i = group; i < nkb; i += kGroupsA) {
             float v[BK];
-            A.row(kb_begin + i, m0 + tg, v);                   // global loads in flight before we block on the stage
+            A.row(kb_begin + i, actx, v);                      // global loads in flight before we block on the stage
             const int s = i % kStagesA;
             const uint32_t it = (uint32_t)(i / kStagesA);
             mbar_wait(a_empty + 8 * s, (it & 1u) ^ 1u);
@@ -245,13 +317,14 @@ gemm_tc2_kernel(ALoad A, BLoad B, Epi epi, int num_kb_total, int kb_per_split) {
             __syncwarp();
             if (lane == 0) mbar_arrive(a_full + 8 * s);
         }
-    } else if (warp < 12) {
-        // ---------------- B loaders: gmem -> registers (one K block ahead) -> swizzled smem hi / lo
-        const int tg = threadIdx.x & 127;
-        BRegs<BN> cur, nxt;
-        if (nkb > 0) B.load(kb_begin, tg, n0, cur);
-        for (int i = 0; i < nkb; ++i) {
-            if (i + 1 < nkb) B.load(kb_begin + i + 1, tg, n0, nxt);
+    } else if (warp < kWarpMma) {
+        // ---------------- B loaders: gmem -> registers -> swizzled smem hi / lo; group g owns K blocks i % kGroupsB == g
+        // (a single B group was the gen-2 bottleneck: ~300 dependent instructions per thread per K block at < 0.25 IPC)
+        const int tg = threadIdx.x & 127, group = (warp - kWarpsA) >> 2;
+        const typename BLoad::Ctx bctx = B.prep(tg, n0);
+        for (int i = group; i < nkb; i += kGroupsB) {
+            BRegs<BN> cur;
+            B.load(kb_begin + i, tg, bctx, cur);                // loads in flight before blocking on the stage
             const int s = i % STAGES_B;
             const uint32_t it = (uint32_t)(i / STAGES_B);
             mbar_wait(b_empty + 8 * s, (it & 1u) ^ 1u);
@@ -260,7 +333,6 @@ gemm_tc2_kernel(ALoad A, BLoad B, Epi epi, int num_kb_total, int kb_per_split) {
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(b_full + 8 * s);
-            cur = nxt;
         }
     } else if (lane == 0) {
         // ---------------- MMA issuer
@@ -315,7 +387,7 @@ gemm_tc2_kernel(ALoad A, BLoad B, Epi epi, int num_kb_total, int kb_per_split) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 12) tmem_dealloc(tmem_base, L::kTmemCols);
+    if (warp == kWarpMma) tmem_dealloc(tmem_base, L::kTmemCols);
 }
 
 template <int BN, int STAGES_B, bool WITH_LO, class ALoad, class BLoad, class Epi>
@@ -341,8 +413,19 @@ int tc2_conv_fwd(const float* x, const float* w2, const float* bias, float* y, i
                  int S, int pad, int relu, bool with_lo, cudaStream_t s) {
     using namespace tc2;
     const int P = H, Q = W, M = N * P * Q;
-    PixelRows A{x, C, H, W, R, S, pad, P, Q, M, FastDiv32(P * Q), FastDiv32(Q), FastDiv32(C), FastDiv32(S)};
     EpiNCHW e{y, bias, relu, M, K, P * Q, FastDiv32(P * Q)};
+    if (C % 32 != 0) {          // small-C first layer: w2 is [K][32] zero-padded, one K block
+        PixelRowsSmallC A{x, C, H, W, R, S, pad, P, Q, M, R * S * C, FastDiv32(P * Q), FastDiv32(Q), FastDiv32(C), FastDiv32(S)};
+        if (K > 64) {
+            WeightRows<128> B{w2, K, 32, 32};
+            dim3 grid((M + BM - 1) / BM, (K + 127) / 128, 1);
+            return with_lo ? launch<128, 4, true>(A, B, e, grid, 1, 1, s) : launch<128, 4, false>(A, B, e, grid, 1, 1, s);
+        }
+        WeightRows<64> B{w2, K, 32, 32};
+        dim3 grid((M + BM - 1) / BM, (K + 63) / 64, 1);
+        return with_lo ? launch<64, 4, true>(A, B, e, grid, 1, 1, s) : launch<64, 4, false>(A, B, e, grid, 1, 1, s);
+    }
+    PixelRows A{x, C, H, W, R, S, pad, P, Q, M, FastDiv32(P * Q), FastDiv32(Q), FastDiv32(C), FastDiv32(S)};
     const int nkb = R * S * C / BK;
     if (K % 128 == 0 || K > 64) {
         WeightRows<128> B{w2, K, (int64_t)R * S * C, R * S * C};

@@ -54,7 +54,7 @@ unsigned long long clb_launch_count(void); /* kernels launched by this library s
  * ---------------------------------------------------------------------------------------- */
 
 /* y = conv2d(x, w) + bias, optional fused ReLU.  nn.Conv2d + nn.ReLU  (models/VGGSlim.py:34-38)
- * w_ws: scratch of K*C*R*S floats for the tensor-core path's re-ordered weights (may be NULL: forces the fp32 path) */
+ * w_ws: scratch of max(K*C*R*S, K*32) floats for the tensor-core path's re-ordered weights (NULL forces the fp32 path) */
 int clb_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, float* w_ws, int N, int C, int H,
                    int W, int K, int R, int S, int stride, int pad, int relu, void* stream);
 /* dx = conv2d_backward_input(dy, w).  wt_ws: scratch of K*C*R*S floats (transposed/flipped weights). */

@@ -1,0 +1,120 @@
+"""GPU: the reference-named per-method entry points end to end (load pickled model -> importance pass -> new head ->
+training -> pickled best model with reg_params), i.e. what `Method.train` / `Method.grid_train` call
+(src/methods/method.py:674-685, 708-716, 737-750, 1006-1025, 383-413).  Checks the plumbing the framework relies on:
+return types, side files, that the pickled model reloads with its reg_params keyed by its own parameters, and that a
+reloaded model continues (task 3) -- plus CUDA-graph replay == eager execution, bit for bit."""
+import os
+import types
+
+import pytest
+import torch
+import torch.nn as nn
+
+from tests.util import BS, NCLS, load_golden, loaders, rel_err, tiny_model
+
+pytestmark = pytest.mark.gpu
+
+
+class DS(torch.utils.data.TensorDataset):
+    classes = list(range(NCLS))
+
+
+def _task(seed, n=64):
+    g = torch.Generator().manual_seed(seed)
+    return DS(torch.randn(n, 3, 16, 16, generator=g), torch.randint(0, NCLS, (n,), generator=g))
+
+
+def _save_task(tmp_path, name, seed):
+    p = str(tmp_path / (name + ".pth"))
+    torch.save({"train": _task(seed), "val": _task(seed + 500, 32)}, p)
+    return p
+
+
+def _first_model(tmp_path):
+    torch.manual_seed(7)
+    m = tiny_model()
+    p = str(tmp_path / "first_task_model.pth.tar")
+    torch.save(m, p)
+    return p
+
+
+@pytest.mark.parametrize("which", ["EWC", "MAS", "SI"])
+def test_method_train_two_tasks(tmp_path, which):
+    from clsurvey_b200.methods import method as M
+    meth = M.parse(which)
+    model_path = _first_model(tmp_path)
+    for task in (2, 3):
+        exp_dir = str(tmp_path / ("task_%d" % task))
+        manager = types.SimpleNamespace(current_task_dataset_path=_save_task(tmp_path, "t%d" % task, 10 + task),
+                                        previous_task_model_path=model_path, heuristic_exp_dir=exp_dir,
+                                        reg_sets=[_save_task(tmp_path, "prev%d" % task, 9 + task)])
+        args = types.SimpleNamespace(data_dir=None, batch_size=BS, num_epochs=2, lr=0.05, weight_decay=0.0,
+                                     saving_freq=1, init_model_path=None)
+        model, acc = meth.train(args, manager, {"lambda": 2.0})
+        assert 0.0 <= acc <= 1.0
+        best = os.path.join(exp_dir, "best_model.pth.tar")
+        assert os.path.isfile(best) and os.path.isfile(os.path.join(exp_dir, "epoch.pth.tar"))
+        assert os.path.isfile(os.path.join(exp_dir, "preprocess_time.pth.tar"))
+        re = torch.load(best, weights_only=False)
+        assert hasattr(re, "reg_params") and re.reg_params["lambda"] == 2.0
+        n_reg = sum(1 for p in re.parameters() if p in re.reg_params)
+        assert n_reg >= len(list(re.parameters())) - 2            # everything but (possibly) the fresh head
+        for p in re.parameters():
+            if p in re.reg_params:
+                assert re.reg_params[p]["omega"].shape == p.shape and torch.isfinite(re.reg_params[p]["omega"]).all()
+        model_path = best
+
+
+def test_finetune_grid_train(tmp_path):
+    from clsurvey_b200.methods import method as M
+    manager = types.SimpleNamespace(current_task_dataset_path=_save_task(tmp_path, "t2", 21),
+                                    previous_task_model_path=_first_model(tmp_path),
+                                    gridsearch_exp_dir=str(tmp_path / "grid"))
+    args = types.SimpleNamespace(batch_size=BS, num_epochs=2, weight_decay=0.0, saving_freq=1)
+    model, acc = M.Finetune.grid_train(args, manager, 0.05)
+    assert os.path.isfile(os.path.join(manager.gridsearch_exp_dir, "best_model.pth.tar")) and 0 <= acc <= 1
+
+
+def test_gem_postprocess_then_train(tmp_path):
+    from clsurvey_b200.methods.rehearsal import main_rehearsal, train_rehearsal
+    base = _first_model(tmp_path)
+    n_tasks, nc = 3, [NCLS] * 3
+    wrapped = str(tmp_path / "gem_task1.pth.tar")
+    common = dict(weight_decay=0.0, task_name="t", n_outputs=sum(nc), method="gem", n_memories=24, n_epochs=2,
+                  memory_strength=0.5, n_tasks=n_tasks, batch_size=BS, lr=0.05, finetune=False)
+    r = main_rehearsal.main(dict(common, task_count=1, prev_model_path=base, save_path=wrapped, is_scratch_model=True,
+                                 postprocess=True, dataset_path=_save_task(tmp_path, "g1", 31)), nc)
+    assert r == (None, None) and os.path.isfile(wrapped)
+    out2 = str(tmp_path / "gem_task2")
+    os.makedirs(out2)
+    model, acc = main_rehearsal.main(dict(common, task_count=2, prev_model_path=wrapped, save_path=out2,
+                                          is_scratch_model=False, postprocess=False,
+                                          dataset_path=_save_task(tmp_path, "g2", 32)), nc)
+    assert 0 <= acc <= 1 and os.path.isfile(os.path.join(out2, "best_model.pth.tar"))
+    assert model.observed_tasks == [0, 1]
+    assert len(train_rehearsal.LAST_RUN["violations"]) == 2 * (64 // BS)
+    re = torch.load(os.path.join(out2, "best_model.pth.tar"), weights_only=False)
+    assert re.memory_labels.shape == (n_tasks, 24) and re.observed_tasks == [0, 1]
+
+
+def test_cuda_graph_replay_equals_eager(tmp_path, monkeypatch):
+    """The trainer replays a captured graph from the third step of a configuration on; results must be bit-identical
+    to fully eager execution."""
+    from clsurvey_b200.engine import Engine
+    from clsurvey_b200.methods import trainers
+    from clsurvey_b200.methods.Finetune import train_SGD
+    from clsurvey_b200.methods.optim import SGD
+    f = load_golden("finetune")["wd5e-4"]
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("CLB_CUDA_GRAPH", flag)
+        m = tiny_model(f["init"])
+        Engine(m, (3, 16, 16), BS)
+        ld, sizes = loaders(f["data"])
+        opt = SGD(m.parameters(), f["lr"], momentum=0.9, weight_decay=f["wd"])
+        m, best = train_SGD.train_model(m, nn.CrossEntropyLoss(), opt, f["lr"], ld, sizes, True, f["epochs"],
+                                        exp_dir=str(tmp_path), resume="", save_models_mode=False)
+        out[flag] = (best, list(trainers.LAST_RUN["batch_losses"]), {k: v.clone() for k, v in m.state_dict().items()})
+    assert out["0"][0] == out["1"][0] and out["0"][1] == out["1"][1]
+    for k in out["0"][2]:
+        assert torch.equal(out["0"][2][k], out["1"][2][k]), k

@@ -281,21 +281,27 @@ gemm_tc_kernel(ALoad A, BLoad B, Epi epi, int num_kb_total, int kb_per_split) {
 
 // ---------------------------------------------------------------------------------------------- helper kernels
 // w[K][C][RS] -> w2[K][ld] with w2[k][rs*C + c]   (forward GEMM-B, K order (r,s,c)); ld > RS*C zero-pads the row
-__global__ void permute_w_fwd_kernel(const float* __restrict__ w, float* __restrict__ w2, int K, int C, int RS, int ld) {
+__global__ void permute_w_fwd_kernel(const float* __restrict__ w, float* __restrict__ w2, float* __restrict__ w2_lo, int K,
+                                     int C, int RS, int ld) {
     const int64_t total = (int64_t)K * ld, gs = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gs) {
         const int j = (int)(i % ld), k = (int)(i / ld);
         const int c = j % C, rs = j / C;
-        w2[i] = (j < RS * C) ? w[((int64_t)k * C + c) * RS + rs] : 0.f;
+        const float v = (j < RS * C) ? w[((int64_t)k * C + c) * RS + rs] : 0.f;
+        w2[i] = v;
+        if (w2_lo) w2_lo[i] = v - __uint_as_float(__float_as_uint(v) & kHiMask);     // TMA-fed kernels read the lo plane
     }
 }
 // w[K][C][R][S] -> wd[C][(R-1-r, S-1-s)][K]   (dgrad = forward conv of dY: rows = c, K order (r', s', kout))
-__global__ void permute_w_dgrad_kernel(const float* __restrict__ w, float* __restrict__ wd, int K, int C, int R, int S) {
+__global__ void permute_w_dgrad_kernel(const float* __restrict__ w, float* __restrict__ wd, float* __restrict__ wd_lo, int K,
+                                       int C, int R, int S) {
     const int64_t total = (int64_t)K * C * R * S, gs = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gs) {
         const int k = (int)(i % K), rs = (int)((i / K) % (R * S)), c = (int)(i / ((int64_t)K * R * S));
         const int r = R - 1 - rs / S, s = S - 1 - rs % S;
-        wd[i] = w[(((int64_t)k * C + c) * R + r) * S + s];
+        const float v = w[(((int64_t)k * C + c) * R + r) * S + s];
+        wd[i] = v;
+        if (wd_lo) wd_lo[i] = v - __uint_as_float(__float_as_uint(v) & kHiMask);
     }
 }
 // dw[K][C][RS] = sum_z ws[z][K][RS][C]   (fixed summation order -> bit-reproducible)
@@ -342,14 +348,35 @@ int tc2_conv_fwd(const float* x, const float* w2, const float* bias, float* y, i
 int tc2_conv_wgrad(const float* x, const float* dy, float* ws, int N, int C, int H, int W, int K, int R, int S, int pad,
                    bool with_lo, cudaStream_t s);
 
-// CLB_TC_IMPL=1 selects the first-generation kernel (both operands through smem); default 2 (A through TMEM)
+size_t tc_w_plane_floats(int K, int C, int R, int S);
+bool tc3_wgrad_supported(int C, int H, int W, int K, int R, int S, int stride, int pad);
+size_t tc3_wgrad_extra_floats(int N, int C, int H, int W, int K);
+int tc3_conv_fwd(const float* x, const float* w2, const float* w2_lo, const float* bias, float* y, int N, int C, int H, int W,
+                 int K, int R, int S, int pad, int relu, bool with_lo, cudaStream_t s);
+int tc3_conv_wgrad(const float* x, const float* dy, float* ws_partials, float* x_lo, float* dy_lo, int N, int C, int H, int W,
+                   int K, int R, int S, int pad, bool with_lo, int splits, int kb_per_split, cudaStream_t s);
+
+// CLB_TC_IMPL: 1 = first generation (both operands gathered into smem), 2 = A through TMEM, 3 (default) = gen-2 plus
+// TMA-fed kernels where the memory layout allows it (wgrad on >= 8x8 maps)
 static int tc_impl() {
     static int v = 0;
     if (v == 0) {
         const char* e = getenv("CLB_TC_IMPL");
-        v = (e && e[0] == '1') ? 1 : 2;
+        v = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 3;
     }
     return v;
+}
+
+static void tc3_wgrad_plan(int N, int C, int H, int W, int K, int R, int S, int* splits, int* kb_per_split) {
+    const int n_rows = R * S * C, nkb = N * H * W / 32;
+    const int64_t tiles = (int64_t)((K + 127) / 128) * ((n_rows + 127) / 128);
+    int64_t want = (2LL * 148 + tiles - 1) / tiles;
+    const int64_t max_splits = (nkb + 15) / 16;
+    if (want > max_splits) want = max_splits;
+    if (want < 1) want = 1;
+    const int per = (int)((nkb + want - 1) / want);
+    *kb_per_split = per;
+    *splits = (nkb + per - 1) / per;
 }
 
 // shapes the tensor-core path takes (everything else stays on the exact-fp32 SIMT kernels):
@@ -361,14 +388,19 @@ static bool same_conv(int H, int W, int R, int S, int stride, int pad) {
 }
 bool tc_fwd_supported(int C, int H, int W, int K, int R, int S, int stride, int pad) {
     if (!same_conv(H, W, R, S, stride, pad)) return false;
-    return (C % 32) == 0 || (tc_impl() == 2 && C * R * S <= 32);
+    if ((C % 32) == 0) return true;
+    // first layer (C*R*S <= 32): one K block per CTA -- the per-CTA prologue (TMEM alloc, barrier init) dominates and the
+    // exact-fp32 SIMT kernel is faster (158 us vs 256 us at batch 200); opt-in only
+    static int small_c = -1;
+    if (small_c < 0) { const char* e = getenv("CLB_TC_SMALLC"); small_c = (e && e[0] == '1') ? 1 : 0; }
+    return small_c && tc_impl() >= 2 && C * R * S <= 32;
 }
 bool tc_dgrad_supported(int C, int H, int W, int K, int R, int S, int stride, int pad) {
     return same_conv(H, W, R, S, stride, pad) && (K % 32) == 0;
 }
 bool tc_wgrad_supported(int C, int H, int W, int K, int R, int S, int stride, int pad) {
     if (!same_conv(H, W, R, S, stride, pad) || (W % 4) != 0) return false;
-    return tc_impl() == 2 || (C % 32) == 0;
+    return tc_impl() >= 2 || (C % 32) == 0;
 }
 
 size_t tc_weight_ws_floats(int C, int K, int R, int S) { return (size_t)K * C * R * S; }
@@ -376,7 +408,13 @@ size_t tc_weight_ws_floats(int C, int K, int R, int S) { return (size_t)K * C * 
 int tc_conv_fwd(const float* x, const float* w2 /*[K][RS][C]*/, const float* bias, float* y, int N, int C, int H, int W,
                 int K, int R, int S, int pad, int relu, bool with_lo, cudaStream_t s) {
     using namespace tc;
-    if (tc_impl() == 2) return tc2_conv_fwd(x, w2, bias, y, N, C, H, W, K, R, S, pad, relu, with_lo, s);
+    if (tc_impl() >= 3) {
+        // w2 holds [hi plane][lo plane]; the plane size was fixed by whoever re-ordered the weights:
+        // fwd: (K outputs, C inputs); dgrad calls us with (C_in := K_out, K_out := C_in) -> the same product K*C*R*S
+        const size_t plane = tc_w_plane_floats(K, C, R, S);
+        return tc3_conv_fwd(x, w2, w2 + plane, bias, y, N, C, H, W, K, R, S, pad, relu, with_lo, s);
+    }
+    if (tc_impl() >= 2) return tc2_conv_fwd(x, w2, bias, y, N, C, H, W, K, R, S, pad, relu, with_lo, s);
     const int P = H, Q = W, M = N * P * Q;
     PixelGather A{x, C, H, W, R, S, pad, P, Q, M, FastDiv32(P * Q), FastDiv32(Q), FastDiv32(C), FastDiv32(S)};
     EpiNCHW e{y, bias, relu, M, K, P * Q, FastDiv32(P * Q)};
@@ -409,7 +447,14 @@ void tc_wgrad_plan(int N, int C, int H, int W, int K, int R, int S, int* bn, int
 size_t tc_wgrad_ws_floats(int N, int C, int H, int W, int K, int R, int S) {
     int bn, splits, per;
     tc_wgrad_plan(N, C, H, W, K, R, S, &bn, &splits, &per);
-    return (size_t)splits * K * C * R * S;
+    size_t need = (size_t)splits * K * C * R * S;
+    if (tc_impl() >= 3 && tc3_wgrad_supported(C, H, W, K, R, S, 1, (R - 1) / 2)) {
+        int s3, p3;
+        tc3_wgrad_plan(N, C, H, W, K, R, S, &s3, &p3);
+        const size_t n3 = (size_t)s3 * K * C * R * S + 8 + tc3_wgrad_extra_floats(N, C, H, W, K);
+        if (n3 > need) need = n3;
+    }
+    return need;
 }
 
 int tc_conv_wgrad(const float* x, const float* dy, float* dw, float* ws, int N, int C, int H, int W, int K, int R, int S,
@@ -417,12 +462,21 @@ int tc_conv_wgrad(const float* x, const float* dy, float* dw, float* ws, int N, 
     using namespace tc;
     const int P = H, Q = W, npix = N * P * Q, n_rows = R * S * C;
     int bn, splits, per;
+    if (tc_impl() >= 3 && tc3_wgrad_supported(C, H, W, K, R, S, 1, pad)) {
+        tc3_wgrad_plan(N, C, H, W, K, R, S, &splits, &per);
+        size_t off = ((size_t)splits * K * n_rows + 7) & ~(size_t)3;              // keep the lo plane 16-byte aligned
+        float* dy_lo = ws + off;
+        int rc3 = tc3_conv_wgrad(x, dy, ws, nullptr, dy_lo, N, C, H, W, K, R, S, pad, with_lo, splits, per, s);
+        if (rc3) return rc3;
+        splitk_reduce_permute_kernel<<<ew_blocks((int64_t)K * n_rows), 256, 0, s>>>(ws, dw, K, C, R * S, splits); clb::count_launch();
+        return CLB_OK;
+    }
     tc_wgrad_plan(N, C, H, W, K, R, S, &bn, &splits, &per);
     const int nkb = (npix + BK - 1) / BK;
     RowsKContig<128> A{dy, K, (int64_t)P * Q, npix, P * Q, (int64_t)K * P * Q, FastDiv32(P * Q)};
     EpiSplitK e{ws, K, n_rows, (int64_t)K * n_rows};
     int rc;
-    if (tc_impl() == 2) {
+    if (tc_impl() >= 2) {
         rc = tc2_conv_wgrad(x, dy, ws, N, C, H, W, K, R, S, pad, with_lo, s);
     } else if (bn == 128) {
         TapRowsOverPixels<128> B{x, C, H, W, R, S, pad, P, Q, n_rows, npix, FastDiv32(P * Q), FastDiv32(Q), FastDiv32(C), FastDiv32(S)};
@@ -438,12 +492,21 @@ int tc_conv_wgrad(const float* x, const float* dy, float* dw, float* ws, int N, 
     return CLB_OK;
 }
 
+// workspace layout for the re-ordered weights: [hi plane: plane floats][lo plane: plane floats], plane = tc_w_plane_floats()
+size_t tc_w_plane_floats(int K, int C, int R, int S) {
+    const size_t a = (size_t)K * C * R * S, b = (size_t)K * 32, c = (size_t)C * 32;
+    size_t m = a > b ? a : b;
+    m = m > c ? m : c;
+    return (m + 3) & ~(size_t)3;
+}
 void tc_permute_w_fwd(const float* w, float* w2, int K, int C, int RS, cudaStream_t s) {
     const int ld = (C % 32 == 0) ? RS * C : 32;
-    tc::permute_w_fwd_kernel<<<tc::ew_blocks((int64_t)K * ld), 256, 0, s>>>(w, w2, K, C, RS, ld); clb::count_launch();
+    float* lo = tc_impl() >= 3 ? w2 + tc_w_plane_floats(K, C, RS, 1) : nullptr;
+    tc::permute_w_fwd_kernel<<<tc::ew_blocks((int64_t)K * ld), 256, 0, s>>>(w, w2, lo, K, C, RS, ld); clb::count_launch();
 }
 void tc_permute_w_dgrad(const float* w, float* wd, int K, int C, int R, int S, cudaStream_t s) {
-    tc::permute_w_dgrad_kernel<<<tc::ew_blocks((int64_t)K * C * R * S), 256, 0, s>>>(w, wd, K, C, R, S); clb::count_launch();
+    float* lo = tc_impl() >= 3 ? wd + tc_w_plane_floats(K, C, R, S) : nullptr;
+    tc::permute_w_dgrad_kernel<<<tc::ew_blocks((int64_t)K * C * R * S), 256, 0, s>>>(w, wd, lo, K, C, R, S); clb::count_launch();
 }
 
 }  // namespace clb

@@ -225,7 +225,8 @@ class Engine:
             if op["kind"] == "conv":
                 ws_bytes = max(ws_bytes, _capi.lib().clb_conv2d_wgrad_ws(B, op["C"], op["H"], op["W"], op["K"], op["R"],
                                                                           op["S"], op["stride"], op["pad"]))
-                wt_elems = max(wt_elems, op["K"] * op["C"] * op["R"] * op["S"], op["K"] * 32)
+                # re-ordered weights for the tensor-core path: hi + lo plane, each max(K*C*R*S, 32*K, 32*C) floats
+                wt_elems = max(wt_elems, 2 * (max(op["K"] * op["C"] * op["R"] * op["S"], op["K"] * 32, op["C"] * 32) + 4))
         self.ws = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=self.device)
         self.wt_ws = torch.empty(wt_elems, dtype=torch.float32, device=self.device)
         self.loss_dev = torch.zeros(1, dtype=torch.float32, device=self.device)

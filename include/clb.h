@@ -54,10 +54,11 @@ unsigned long long clb_launch_count(void); /* kernels launched by this library s
  * ---------------------------------------------------------------------------------------- */
 
 /* y = conv2d(x, w) + bias, optional fused ReLU.  nn.Conv2d + nn.ReLU  (models/VGGSlim.py:34-38)
- * w_ws: scratch of max(K*C*R*S, K*32) floats for the tensor-core path's re-ordered weights (NULL forces the fp32 path) */
+ * w_ws: scratch of 2*max(K*C*R*S, 32*K, 32*C)+8 floats for the tensor-core path's re-ordered weight planes (hi, lo);
+ *       NULL forces the fp32 path */
 int clb_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, float* w_ws, int N, int C, int H,
                    int W, int K, int R, int S, int stride, int pad, int relu, void* stream);
-/* dx = conv2d_backward_input(dy, w).  wt_ws: scratch of K*C*R*S floats (transposed/flipped weights). */
+/* dx = conv2d_backward_input(dy, w).  wt_ws: scratch sized like clb_conv2d_fwd's w_ws (transposed/flipped weight planes). */
 int clb_conv2d_dgrad(const float* dy, const float* w, float* dx, float* wt_ws, int N, int C, int H, int W, int K,
                      int R, int S, int stride, int pad, void* stream);
 /* dw = conv2d_backward_weight(x, dy), dbias = sum dy.  ws: split-K partials, ws_bytes >= clb_conv2d_wgrad_ws(...) */
@@ -155,6 +156,11 @@ int clb_nccl_unique_id(void* out128);                              /* rank 0: 12
 int clb_nccl_init(const void* id128, int rank, int world, void** comm_out);
 int clb_nccl_allreduce_f32(void* comm, float* buf, int64_t n, void* stream);
 int clb_nccl_destroy(void* comm);
+
+/* diagnostic (bring-up of the MN-major shared-memory descriptor); not part of the hot path */
+int clb_debug_umma_mn(const float* At, const float* B, float* D, int variant, void* stream);
+int clb_debug_tma3d(const float* x, int d0, int d1, int d2, int b0, int b1, int b2, int swizzle, int c0, int c1, int c2,
+                    float* out, void* stream);
 
 #ifdef __cplusplus
 }

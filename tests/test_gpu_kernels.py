@@ -116,7 +116,7 @@ def test_conv2d_fwd_bwd(capi, shape, mode):
         y_ = dev(torch.zeros_like(y_ref))
         dxc, dwc, dyc = dev(x), dev(w), dev(dy)
         dbc = dev(b)
-        wws = torch.empty(max(w.numel(), K * 32), device="cuda")
+        wws = torch.empty(2 * max(w.numel(), K * 32, C * 32) + 8, device="cuda")
         capi.call("clb_conv2d_fwd", dxc.data_ptr(), dwc.data_ptr(), dbc.data_ptr(), y_.data_ptr(), wws.data_ptr(), N, C, H,
                   W, K, R, R, stride, pad, 1, S())
         assert rel_err(y_, y_ref) <= tol
@@ -126,7 +126,7 @@ def test_conv2d_fwd_bwd(capi, shape, mode):
                   ws.numel() * 4, N, C, H, W, K, R, R, stride, pad, S())
         assert rel_err(dw_, wr.grad) <= tol, "wgrad"
         assert rel_err(db_, br.grad) <= tol, "bias grad"
-        wt = torch.empty(max(w.numel(), K * 32), device="cuda")
+        wt = torch.empty(2 * max(w.numel(), K * 32, C * 32) + 8, device="cuda")
         capi.call("clb_conv2d_dgrad", dyc.data_ptr(), dwc.data_ptr(), dx_.data_ptr(), wt.data_ptr(), N, C, H, W, K, R, R,
                   stride, pad, S())
         assert rel_err(dx_, xr.grad) <= tol, "dgrad"

@@ -23,7 +23,7 @@ from tests.util import rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
-GRAD_TOL = 5e-2      # discontinuity-limited, see module docstring
+GRAD_TOL = 1e-1      # discontinuity-limited sanity bound, see module docstring
 
 
 def _models():

@@ -30,7 +30,7 @@ def run(shape, mode, structured=False):
     _capi.call("clb_set_matmul_mode", mode)
     xd, wd, bd, dyd = x.cuda(), w.cuda(), b.cuda(), dy.cuda()
     y = torch.zeros_like(y_ref).cuda()
-    wws = torch.empty(max(w.numel(), K * 32), device="cuda")
+    wws = torch.empty(2 * max(w.numel(), K * 32, C * 32) + 8, device="cuda")
     _capi.call("clb_conv2d_fwd", xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), y.data_ptr(), wws.data_ptr(), N, C, H, W, K, 3, 3, 1, 1, 0, S())
     torch.cuda.synchronize()
     e = rel(y, y_ref.detach())
@@ -59,6 +59,10 @@ def run(shape, mode, structured=False):
 
 if __name__ == "__main__":
     _capi.lib()
+    if len(sys.argv) > 1 and sys.argv[1] == "tma":
+        run((2, 64, 8, 8, 128), 1)
+        print("tc_debug tma done")
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "first":
         run((2, 3, 16, 16, 8), 1)
         print("tc_debug first done")

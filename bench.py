@@ -162,6 +162,9 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------------------------- GPU arm
 def run_gpu_arm(args):
+    # native libraries (NCCL prints its version banner) write to fd 1: keep the real stdout for the ONE JSON line
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     from clsurvey_b200 import _capi, dist as cdist
     from clsurvey_b200.engine import Engine
     from clsurvey_b200.methods.optim import Weight_Regularized_SGD
@@ -196,7 +199,7 @@ def run_gpu_arm(args):
         eng.fwd_loss_bwd(xb, yb, denom=GLOBAL_BATCH, train=True)
         opt.step(model.reg_params)
 
-    use_graph = (not args.no_graph) and world == 1
+    use_graph = (not args.no_graph) and (world == 1 or args.graph_dp)   # NCCL calls are capturable; opt-in for N > 1
     state = {"run": None}
 
     def step_eager(i):
@@ -325,7 +328,7 @@ def run_gpu_arm(args):
             "roofline_fisher": fisher,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     cdist.shutdown()
 
 
@@ -339,6 +342,7 @@ def main():
     ap.add_argument("--mm-mode", type=int, default=int(os.environ.get("CLB_MM_MODE", "0")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--graph-dp", action="store_true", help="capture the step (incl. the NCCL all-reduce) in a CUDA graph for N > 1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "clb" else args.warmup
     if args.impl == "reference":

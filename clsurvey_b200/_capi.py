@@ -26,9 +26,10 @@ SIGNATURES = {
     "clb_conv2d_dgrad": [c_p, c_p, c_p, c_p] + [c_i] * 9 + [c_p],
     "clb_conv2d_wgrad_ws": [c_i] * 9,
     "clb_conv2d_wgrad": [c_p, c_p, c_p, c_p, c_p, c_sz] + [c_i] * 9 + [c_p],
-    "clb_linear_fwd": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
-    "clb_linear_dgrad": [c_p, c_p, c_p, c_i, c_i, c_i, c_p],
-    "clb_linear_wgrad": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p],
+    "clb_linear_ws": [c_i, c_i, c_i],
+    "clb_linear_fwd": [c_p, c_p, c_p, c_p, c_p, c_sz, c_i, c_i, c_i, c_i, c_p],
+    "clb_linear_dgrad": [c_p, c_p, c_p, c_p, c_sz, c_i, c_i, c_i, c_p],
+    "clb_linear_wgrad": [c_p, c_p, c_p, c_p, c_p, c_sz, c_i, c_i, c_i, c_p],
     "clb_relu_bwd": [c_p, c_p, c_p, c_i64, c_p],
     "clb_maxpool_fwd": [c_p, c_p, c_p] + [c_i] * 6 + [c_p],
     "clb_maxpool_bwd": [c_p, c_p, c_p, c_p] + [c_i] * 6 + [c_p],
@@ -53,7 +54,7 @@ SIGNATURES = {
     "clb_nccl_allreduce_f32": [c_p, c_p, c_i64, c_p],
     "clb_nccl_destroy": [c_p],
 }
-_RESTYPE = {"clb_last_error": ctypes.c_char_p, "clb_conv2d_wgrad_ws": c_sz, "clb_launch_count": ctypes.c_ulonglong}
+_RESTYPE = {"clb_last_error": ctypes.c_char_p, "clb_conv2d_wgrad_ws": c_sz, "clb_launch_count": ctypes.c_ulonglong, "clb_linear_ws": c_sz}
 
 
 class ClbError(RuntimeError):

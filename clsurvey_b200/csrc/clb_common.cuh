@@ -63,6 +63,12 @@ int tc_conv_fwd(const float* x, const float* w2, const float* bias, float* y, in
 size_t tc_wgrad_ws_floats(int N, int C, int H, int W, int K, int R, int S);
 int tc_conv_wgrad(const float* x, const float* dy, float* dw, float* ws, int N, int C, int H, int W, int K, int R, int S,
                   int pad, bool with_lo, cudaStream_t s);
+bool tc3_linear_supported(int M, int in, int out);
+size_t tc3_linear_ws_floats(int M, int in, int out);
+int tc3_linear_fwd(const float* x, const float* w, const float* bias, float* y, float* ws, int M, int in, int out, int relu,
+                   bool with_lo, cudaStream_t s);
+int tc3_linear_dgrad(const float* dy, const float* w, float* dx, float* ws, int M, int in, int out, bool with_lo, cudaStream_t s);
+int tc3_linear_wgrad(const float* x, const float* dy, float* dw, float* ws, int M, int in, int out, bool with_lo, cudaStream_t s);
 void tc_permute_w_fwd(const float* w, float* w2, int K, int C, int RS, cudaStream_t s);
 void tc_permute_w_dgrad(const float* w, float* wd, int K, int C, int R, int S, cudaStream_t s);
 

@@ -8,6 +8,8 @@
 //     conv fwd :  Y[pix, kout]   = sum_crs  im2col(X)[pix, crs] * W[kout, crs]
 //     conv wgrad: dW[kout, crs]  = sum_pix  dY[kout, pix]      * im2col(X)[pix, crs]      (split-K, 2-pass, deterministic)
 //     conv dgrad (stride 1) = conv fwd of dY with flipped/transposed weights
+#include <stdlib.h>
+
 #include "clb_common.cuh"
 
 namespace clb {
@@ -559,10 +561,25 @@ int clb_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias, f
     return CLB_OK;
 }
 
-int clb_linear_fwd(const float* x, const float* w, const float* bias, float* y, int M, int in, int out, int relu,
-                   void* stream) {
+size_t clb_linear_ws(int M, int in, int out) { return tc3_linear_ws_floats(M, in, out) * sizeof(float); }
+
+static bool linear_on_tc(const float* ws, size_t ws_bytes, int M, int in, int out) {
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("CLB_TC_LINEAR"); enabled = (e && e[0] == '0') ? 0 : 1; }
+    return enabled && mm_mode() != CLB_MM_FP32_SIMT && ws != nullptr && tc3_linear_supported(M, in, out) &&
+           ws_bytes >= tc3_linear_ws_floats(M, in, out) * sizeof(float);
+}
+
+int clb_linear_fwd(const float* x, const float* w, const float* bias, float* y, float* ws, size_t ws_bytes, int M, int in,
+                   int out, int relu, void* stream) {
     CLB_CHECK_ARG(x && w && y && M > 0 && in > 0 && out > 0);
     cudaStream_t s = as_stream(stream);
+    if (linear_on_tc(ws, ws_bytes, M, in, out)) {
+        int rc = tc3_linear_fwd(x, w, bias, y, ws, M, in, out, relu, mm_mode() == CLB_MM_TF32X3, s);
+        if (rc) return rc;
+        CLB_CHECK_LAUNCH();
+        return CLB_OK;
+    }
     StridedMat A{x, in, 1, M, in};
     StridedMat B{w, in, 1, out, in};
     EpiRM e; e.c = y; e.ldc = out; e.bias = bias; e.relu = relu; e.M = M; e.N = out;
@@ -577,9 +594,16 @@ int clb_linear_fwd(const float* x, const float* w, const float* bias, float* y, 
     return CLB_OK;
 }
 
-int clb_linear_dgrad(const float* dy, const float* w, float* dx, int M, int in, int out, void* stream) {
+int clb_linear_dgrad(const float* dy, const float* w, float* dx, float* ws, size_t ws_bytes, int M, int in, int out,
+                     void* stream) {
     CLB_CHECK_ARG(dy && w && dx && M > 0 && in > 0 && out > 0);
     cudaStream_t s = as_stream(stream);
+    if (linear_on_tc(ws, ws_bytes, M, in, out)) {
+        int rc = tc3_linear_dgrad(dy, w, dx, ws, M, in, out, mm_mode() == CLB_MM_TF32X3, s);
+        if (rc) return rc;
+        CLB_CHECK_LAUNCH();
+        return CLB_OK;
+    }
     StridedMat A{dy, out, 1, M, out};        // element(m, o)
     StridedMat B{w, 1, in, in, out};         // element(n = i, k = o) = w[o*in + i]
     EpiRM e; e.c = dx; e.ldc = in; e.bias = nullptr; e.relu = 0; e.M = M; e.N = in;
@@ -589,9 +613,20 @@ int clb_linear_dgrad(const float* dy, const float* w, float* dx, int M, int in, 
     return CLB_OK;
 }
 
-int clb_linear_wgrad(const float* x, const float* dy, float* dw, float* dbias, int M, int in, int out, void* stream) {
+int clb_linear_wgrad(const float* x, const float* dy, float* dw, float* dbias, float* ws, size_t ws_bytes, int M, int in,
+                     int out, void* stream) {
     CLB_CHECK_ARG(x && dy && dw && M > 0 && in > 0 && out > 0);
     cudaStream_t s = as_stream(stream);
+    if (linear_on_tc(ws, ws_bytes, M, in, out)) {
+        int rc = tc3_linear_wgrad(x, dy, dw, ws, M, in, out, mm_mode() == CLB_MM_TF32X3, s);
+        if (rc) return rc;
+        CLB_CHECK_LAUNCH();
+        if (dbias) {
+            linear_bias_grad_kernel<<<(out + 127) / 128, 128, 0, s>>>(dy, dbias, M, out); clb::count_launch();
+            CLB_CHECK_LAUNCH();
+        }
+        return CLB_OK;
+    }
     StridedMat A{dy, 1, out, out, M};        // element(m' = o, k = m) = dy[m*out + o]
     StridedMat B{x, 1, in, in, M};           // element(n = i, k = m) = x[m*in + i]
     EpiRM e; e.c = dw; e.ldc = in; e.bias = nullptr; e.relu = 0; e.M = out; e.N = in;

@@ -340,6 +340,137 @@ wgrad_mixed_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_cons
     if (warp == kMxWarpMma) tmem_dealloc(tmem, kCols);
 }
 
+// ---------------------------------------------------------------------------------------------- plain GEMM, all-TMA (Linear layers)
+// C[M][N] = act(A[M][K] * B[N][K]^T + bias): both operands are K-major row-major matrices, i.e. exactly what a 2-D tensor
+// map describes -- no gather warps at all.  warp 0 = TMA producer (A, A_lo, B, B_lo boxes of 128 x 32), warp 1 = MMA
+// issuer (3-pass split, two TMEM accumulators), warps 2-5 = epilogue.  nn.Linear fwd / dgrad / wgrad map onto it through
+// (small) transposed copies; see clb_linear_* in clb_gemm_simt.cu.
+constexpr int kGmStages = 3;
+constexpr int kGmThreads = 192;
+constexpr int kGmStage = 4 * kTile;
+constexpr int kGmSmem = kGmStages * kGmStage + 256 + 1024;
+
+struct EpiRowMajor {
+    float* c; int64_t ldc; const float* bias; int relu, M, N;
+    __device__ __forceinline__ void store16(int m, int n0, const uint32_t (&r)[16], int) const {
+        if (m >= M) return;
+        float* dst = c + (int64_t)m * ldc + n0;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            v[j] = __uint_as_float(r[j]) + ((bias && n0 + j < N) ? __ldg(bias + n0 + j) : 0.f);
+            if (relu) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (n0 + 15 < N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (n0 + j < N) dst[j] = v[j];
+        }
+    }
+};
+
+template <bool WITH_LO>
+__global__ void __launch_bounds__(kGmThreads, 1)
+gemm_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a_lo,
+                const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_b_lo, EpiRowMajor epi, int nkb) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar = base + kGmStages * kGmStage;
+    const uint32_t full = bar, empty = bar + 8 * kGmStages, bar_tmem = empty + 8 * kGmStages, slot = bar_tmem + 8;
+    uint32_t* slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (slot - smem_u32(smem_raw)));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * 128;
+    constexpr uint32_t kCols = WITH_LO ? 256 : 128;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGmStages; ++s) { mbar_init(full + 8 * s, 1); mbar_init(empty + 8 * s, 1); }
+        mbar_init(bar_tmem, 1);
+        fence_barrier_init();
+        tma::prefetch_desc(&map_a); tma::prefetch_desc(&map_b);
+    }
+    if (warp == 1) tmem_alloc(slot, kCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *slot_ptr;
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % kGmStages;
+            mbar_wait(empty + 8 * s, (((uint32_t)(i / kGmStages)) & 1u) ^ 1u);
+            tma::mbar_arrive_expect_tx(full + 8 * s, (uint32_t)((WITH_LO ? 4 : 2) * kTile));
+            const uint32_t st = base + (uint32_t)s * kGmStage;
+            tma::load_2d(st, &map_a, full + 8 * s, i * BK, m0);
+            tma::load_2d(st + 2 * kTile, &map_b, full + 8 * s, i * BK, n0);
+            if (WITH_LO) {
+                tma::load_2d(st + kTile, &map_a_lo, full + 8 * s, i * BK, m0);
+                tma::load_2d(st + 3 * kTile, &map_b_lo, full + 8 * s, i * BK, n0);
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        constexpr uint32_t idesc = make_idesc(128);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % kGmStages;
+            mbar_wait(full + 8 * s, ((uint32_t)(i / kGmStages)) & 1u);
+            tc_fence_after();
+            const uint32_t st = base + (uint32_t)s * kGmStage;
+            const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + kTile);
+            const uint64_t b_hi = make_desc(st + 2 * kTile), b_lo = make_desc(st + 3 * kTile);
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) {
+                if (WITH_LO) {
+                    umma_tf32(tmem + 128, a_lo + 2 * k, b_hi + 2 * k, idesc, (i | k) != 0);
+                    umma_tf32(tmem + 128, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+                }
+                umma_tf32(tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (i | k) != 0);
+            }
+            umma_commit(empty + 8 * s);
+        }
+        umma_commit(bar_tmem);
+    } else if (warp >= 2) {
+        mbar_wait(bar_tmem, 0);
+        tc_fence_after();
+        const int lane_grp = warp & 3;
+        const int m = m0 + lane_grp * 32 + lane;
+#pragma unroll 1
+        for (int col = 0; col < 128; col += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)col, r);
+            if (WITH_LO) {
+                uint32_t r2[16];
+                tmem_ld16(tmem + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(128 + col), r2);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+            }
+            epi.store16(m, n0 + col, r, 0);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, kCols);
+}
+
+// out[j][i] (row pitch ldo) = in[i][j] (rows x cols, row pitch ldi); optional lo plane of the transposed matrix
+__global__ void transpose_split_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ out_lo,
+                                       int rows, int cols, int ldi, int ldo) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < rows && c < cols) ? in[(int64_t)r * ldi + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + threadIdx.x;          // output row = input column
+        if (c < cols && r < ldo) {
+            const float v = r < rows ? tile[threadIdx.x][i] : 0.f;
+            out[(int64_t)c * ldo + r] = v;
+            if (out_lo) out_lo[(int64_t)c * ldo + r] = v - __uint_as_float(__float_as_uint(v) & kHiMask);
+        }
+    }
+}
+
 static inline int ew_blocks(int64_t n) {
     int64_t b = (n + 255) / 256, cap = (int64_t)sm_count() * 8;
     return (int)(b > cap ? cap : (b < 1 ? 1 : b));
@@ -408,6 +539,88 @@ int tc3_conv_wgrad(const float* x, const float* dy, float* ws_partials, float* /
         wgrad_mixed_kernel<false><<<grid, kMxThreads, kMxSmem, s>>>(m_dy, m_dy_lo, B, e, PQ / 32, npix / 32, kb_per_split); clb::count_launch();
     }
     return CLB_OK;
+}
+
+// ---- Linear layers on the TMA GEMM ------------------------------------------------------------------------------
+static int gemm_tma(const float* A, const float* A_lo, int64_t lda, const float* B, const float* B_lo, int64_t ldb, float* C,
+                    int64_t ldc, const float* bias, int relu, int M, int N, int K, bool with_lo, cudaStream_t s) {
+    using namespace tc3;
+    CUtensorMap ma, mal, mb, mbl;
+    const uint32_t box[2] = {32, 128};
+    {
+        const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+        const uint64_t str[1] = {(uint64_t)lda * 4};
+        int rc = tma::encode_f32(&ma, A, 2, dims, str, box, true);
+        if (rc) return rc;
+        rc = tma::encode_f32(&mal, with_lo ? A_lo : A, 2, dims, str, box, true);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+        const uint64_t str[1] = {(uint64_t)ldb * 4};
+        int rc = tma::encode_f32(&mb, B, 2, dims, str, box, true);
+        if (rc) return rc;
+        rc = tma::encode_f32(&mbl, with_lo ? B_lo : B, 2, dims, str, box, true);
+        if (rc) return rc;
+    }
+    EpiRowMajor e{C, ldc, bias, relu, M, N};
+    dim3 grid((M + BM - 1) / BM, (N + 127) / 128, 1);
+    const int nkb = (K + BK - 1) / BK;
+    static bool configured[2] = {false, false};
+    if (with_lo) {
+        if (!configured[1]) { CLB_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGmSmem)); configured[1] = true; }
+        gemm_tma_kernel<true><<<grid, kGmThreads, kGmSmem, s>>>(ma, mal, mb, mbl, e, nkb); clb::count_launch();
+    } else {
+        if (!configured[0]) { CLB_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGmSmem)); configured[0] = true; }
+        gemm_tma_kernel<false><<<grid, kGmThreads, kGmSmem, s>>>(ma, mal, mb, mbl, e, nkb); clb::count_launch();
+    }
+    return CLB_OK;
+}
+
+static inline size_t r4(size_t n) { return (n + 3) & ~(size_t)3; }
+static void split_lo(const float* x, float* lo, int64_t n, cudaStream_t s) {
+    tc3::split_lo_kernel<<<tc3::ew_blocks(n >> 2), 256, 0, s>>>(x, lo, n); clb::count_launch();
+}
+static void transpose_split(const float* in, float* out, float* out_lo, int rows, int cols, int ldi, int ldo, cudaStream_t s) {
+    dim3 grid((cols + 31) / 32, (ldo + 31) / 32), block(32, 8);
+    tc3::transpose_split_kernel<<<grid, block, 0, s>>>(in, out, out_lo, rows, cols, ldi, ldo); clb::count_launch();
+}
+
+bool tc3_linear_supported(int M, int in, int out) { return (in % 4) == 0 && (out % 4) == 0 && in >= 32; }
+// workspace floats for the three Linear passes (the largest is used for all)
+size_t tc3_linear_ws_floats(int M, int in, int out) {
+    const size_t ldm = r4((size_t)M), ldo = r4((size_t)out);
+    const size_t fwd = r4((size_t)M * in) + r4((size_t)out * in);
+    const size_t dgr = r4((size_t)M * out) + 2 * r4((size_t)in * ldo);
+    const size_t wgr = 2 * r4((size_t)out * ldm) + 2 * r4((size_t)in * ldm);
+    size_t m = fwd > dgr ? fwd : dgr;
+    return (m > wgr ? m : wgr) + 16;
+}
+int tc3_linear_fwd(const float* x, const float* w, const float* bias, float* y, float* ws, int M, int in, int out, int relu,
+                   bool with_lo, cudaStream_t s) {
+    float* x_lo = ws;
+    float* w_lo = ws + r4((size_t)M * in);
+    if (with_lo) { split_lo(x, x_lo, (int64_t)M * in, s); split_lo(w, w_lo, (int64_t)out * in, s); }
+    return gemm_tma(x, x_lo, in, w, w_lo, in, y, out, bias, relu, M, out, in, with_lo, s);
+}
+int tc3_linear_dgrad(const float* dy, const float* w, float* dx, float* ws, int M, int in, int out, bool with_lo, cudaStream_t s) {
+    const int ldo = (int)r4((size_t)out);
+    float* dy_lo = ws;
+    float* wt = ws + r4((size_t)M * out);
+    float* wt_lo = wt + r4((size_t)in * ldo);
+    if (with_lo) split_lo(dy, dy_lo, (int64_t)M * out, s);
+    transpose_split(w, wt, with_lo ? wt_lo : nullptr, out, in, in, ldo, s);          // W[out][in] -> Wt[in][ldo]
+    return gemm_tma(dy, dy_lo, out, wt, wt_lo, ldo, dx, in, nullptr, 0, M, in, out, with_lo, s);
+}
+int tc3_linear_wgrad(const float* x, const float* dy, float* dw, float* ws, int M, int in, int out, bool with_lo, cudaStream_t s) {
+    const int ldm = (int)r4((size_t)M);
+    float* dyt = ws;
+    float* dyt_lo = dyt + r4((size_t)out * ldm);
+    float* xt = dyt_lo + r4((size_t)out * ldm);
+    float* xt_lo = xt + r4((size_t)in * ldm);
+    transpose_split(dy, dyt, with_lo ? dyt_lo : nullptr, M, out, out, ldm, s);       // dY[M][out] -> dYt[out][ldm]
+    transpose_split(x, xt, with_lo ? xt_lo : nullptr, M, in, in, ldm, s);            // X[M][in]   -> Xt[in][ldm]
+    return gemm_tma(dyt, dyt_lo, ldm, xt, xt_lo, ldm, dw, in, nullptr, 0, out, in, M, with_lo, s);
 }
 
 }  // namespace clb

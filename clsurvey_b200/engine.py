@@ -227,6 +227,9 @@ class Engine:
                                                                           op["S"], op["stride"], op["pad"]))
                 # re-ordered weights for the tensor-core path: hi + lo plane, each max(K*C*R*S, 32*K, 32*C) floats
                 wt_elems = max(wt_elems, 2 * (max(op["K"] * op["C"] * op["R"] * op["S"], op["K"] * 32, op["C"] * 32) + 4))
+        for op in ops:
+            if op["kind"] == "linear":
+                ws_bytes = max(ws_bytes, _capi.lib().clb_linear_ws(B, op["inf"], op["outf"]))
         self.ws = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=self.device)
         self.wt_ws = torch.empty(wt_elems, dtype=torch.float32, device=self.device)
         self.loss_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
@@ -265,8 +268,8 @@ class Engine:
                 cur = op["out"]
             elif k == "linear":
                 call("clb_linear_fwd", _ptr(cur), _ptr(self.view(self.theta, op["w"])),
-                     _ptr(self.view(self.theta, op["b"])) if op["b"] is not None else 0, _ptr(op["out"]), n, op["inf"],
-                     op["outf"], int(op["relu"]), s)
+                     _ptr(self.view(self.theta, op["b"])) if op["b"] is not None else 0, _ptr(op["out"]),
+                     _ptr(self.ws), self.ws.numel() * 4, n, op["inf"], op["outf"], int(op["relu"]), s)
                 cur = op["out"]
             elif k == "dropout":
                 if not train:
@@ -326,11 +329,12 @@ class Engine:
                 if op["relu"]:
                     call("clb_relu_bwd", _ptr(d), _ptr(op["out"]), _ptr(d), n * op["outf"], s)
                 call("clb_linear_wgrad", _ptr(op["inp"]), _ptr(d), _ptr(self.view(gdst, op["w"])),
-                     _ptr(self.view(gdst, op["b"])) if op["b"] is not None else 0, n, op["inf"], op["outf"], s)
+                     _ptr(self.view(gdst, op["b"])) if op["b"] is not None else 0, _ptr(self.ws), self.ws.numel() * 4,
+                     n, op["inf"], op["outf"], s)
                 if i != first_param_op:
                     nxt = self.dbuf[other]
-                    call("clb_linear_dgrad", _ptr(d), _ptr(self.view(self.theta, op["w"])), _ptr(nxt), n, op["inf"],
-                         op["outf"], s)
+                    call("clb_linear_dgrad", _ptr(d), _ptr(self.view(self.theta, op["w"])), _ptr(nxt), _ptr(self.ws),
+                         self.ws.numel() * 4, n, op["inf"], op["outf"], s)
                     d, other = nxt, other ^ 1
                 self.n_launch += 3
             elif k == "dropout":

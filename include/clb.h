@@ -67,10 +67,15 @@ int clb_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias, f
                      int C, int H, int W, int K, int R, int S, int stride, int pad, void* stream);
 
 /* y[M,out] = x[M,in] @ w[out,in]^T + bias, optional ReLU.  nn.Linear (+ReLU)  (VGGSlim.py:58-73) */
-int clb_linear_fwd(const float* x, const float* w, const float* bias, float* y, int M, int in, int out, int relu,
-                   void* stream);
-int clb_linear_dgrad(const float* dy, const float* w, float* dx, int M, int in, int out, void* stream);
-int clb_linear_wgrad(const float* x, const float* dy, float* dw, float* dbias, int M, int in, int out, void* stream);
+/* ws / ws_bytes: scratch for the tensor-core path (lo planes, transposed copies), >= clb_linear_ws(M,in,out) bytes;
+ * NULL / too small selects the exact-fp32 path */
+size_t clb_linear_ws(int M, int in, int out);
+int clb_linear_fwd(const float* x, const float* w, const float* bias, float* y, float* ws, size_t ws_bytes, int M, int in,
+                   int out, int relu, void* stream);
+int clb_linear_dgrad(const float* dy, const float* w, float* dx, float* ws, size_t ws_bytes, int M, int in, int out,
+                     void* stream);
+int clb_linear_wgrad(const float* x, const float* dy, float* dw, float* dbias, float* ws, size_t ws_bytes, int M, int in,
+                     int out, void* stream);
 
 /* dx = dy * (y > 0)   (ReLU backward from the saved OUTPUT; in place allowed: dx == dy) */
 int clb_relu_bwd(const float* dy, const float* y, float* dx, int64_t n, void* stream);

@@ -151,10 +151,14 @@ def test_linear_fwd_bwd(capi, M, inf, outf, mode):
         dx, dw, dyc, db = dev(x), dev(w), dev(dy), dev(b)
         y_ = torch.zeros(M, outf, device="cuda")
         gx, gw, gb = torch.zeros(M, inf, device="cuda"), torch.zeros(outf, inf, device="cuda"), torch.zeros(outf, device="cuda")
-        capi.call("clb_linear_fwd", dx.data_ptr(), dw.data_ptr(), db.data_ptr(), y_.data_ptr(), M, inf, outf, 1, S())
+        ws = torch.empty(capi.lib().clb_linear_ws(M, inf, outf) // 4 + 4, device="cuda")
+        wsb = ws.numel() * 4
+        capi.call("clb_linear_fwd", dx.data_ptr(), dw.data_ptr(), db.data_ptr(), y_.data_ptr(), ws.data_ptr(), wsb, M, inf,
+                  outf, 1, S())
         assert rel_err(y_, y_ref) <= tol
-        capi.call("clb_linear_wgrad", dx.data_ptr(), dyc.data_ptr(), gw.data_ptr(), gb.data_ptr(), M, inf, outf, S())
-        capi.call("clb_linear_dgrad", dyc.data_ptr(), dw.data_ptr(), gx.data_ptr(), M, inf, outf, S())
+        capi.call("clb_linear_wgrad", dx.data_ptr(), dyc.data_ptr(), gw.data_ptr(), gb.data_ptr(), ws.data_ptr(), wsb, M, inf,
+                  outf, S())
+        capi.call("clb_linear_dgrad", dyc.data_ptr(), dw.data_ptr(), gx.data_ptr(), ws.data_ptr(), wsb, M, inf, outf, S())
         assert rel_err(gw, wr.grad) <= tol and rel_err(gb, br.grad) <= tol and rel_err(gx, xr.grad) <= tol
     finally:
         capi.call("clb_set_matmul_mode", 0)

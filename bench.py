@@ -199,7 +199,9 @@ def run_gpu_arm(args):
         eng.fwd_loss_bwd(xb, yb, denom=GLOBAL_BATCH, train=True)
         opt.step(model.reg_params)
 
-    use_graph = (not args.no_graph) and (world == 1 or args.graph_dp)   # NCCL calls are capturable; opt-in for N > 1
+    has_dropout = any(op["kind"] == "dropout" for op in eng.ops)
+    eng.dropout_rng = "device"                          # AlexNet: masks drawn on the device (parity tests use host masks)
+    use_graph = (not args.no_graph) and (world == 1 or args.graph_dp) and not has_dropout
     state = {"run": None}
 
     def step_eager(i):
@@ -339,7 +341,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="clb", choices=["clb", "reference"])
     ap.add_argument("--model", default="VGG11_cl_512_512")
-    ap.add_argument("--mm-mode", type=int, default=int(os.environ.get("CLB_MM_MODE", "0")))
+    ap.add_argument("--mm-mode", type=int, default=int(os.environ.get("CLB_MM_MODE", "1")),
+                    help="0 exact-fp32 FFMA, 1 tcgen05 TF32x3 (fp32-parity mode, default), 2 tcgen05 TF32x1 (fast, non-parity)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--graph-dp", action="store_true", help="capture the step (incl. the NCCL all-reduce) in a CUDA graph for N > 1")

@@ -1,11 +1,13 @@
 // Error string, version, device queries.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "clb_common.cuh"
 
 namespace clb {
 static thread_local char g_err[512] = "";
-static int g_mm_mode = CLB_MM_FP32_SIMT;
+// default: tensor-core parity mode (3-pass TF32 split); CLB_MM_MODE=0/1/2 overrides at first use
+static int g_mm_mode = -1;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -26,7 +28,13 @@ int sm_count() {
     }
     return cached;
 }
-int mm_mode() { return g_mm_mode; }
+int mm_mode() {
+    if (g_mm_mode < 0) {
+        const char* e = getenv("CLB_MM_MODE");
+        g_mm_mode = (e && e[0] >= '0' && e[0] <= '2' && e[1] == 0) ? (e[0] - '0') : CLB_MM_TF32X3;
+    }
+    return g_mm_mode;
+}
 static unsigned long long g_launches = 0;
 void count_launch() { ++g_launches; }
 unsigned long long launches() { return g_launches; }
@@ -48,6 +56,6 @@ int clb_set_matmul_mode(int mode) {
     clb::g_mm_mode = mode;
     return CLB_OK;
 }
-int clb_get_matmul_mode(void) { return clb::g_mm_mode; }
+int clb_get_matmul_mode(void) { return clb::mm_mode(); }
 unsigned long long clb_launch_count(void) { return clb::launches(); }
 }

@@ -292,6 +292,8 @@ class Engine:
         """Element mask from the HOST torch generator: F.dropout(x, p) == x * bernoulli(1-p)/(1-p) under the same seed
         (SURVEY.md hard part 4) -- the engine receives masks, it does not regenerate them."""
         keep = 1.0 - op["p"]
+        if getattr(self, "dropout_rng", "host") == "device":      # throughput mode: no per-step H2D of the masks
+            return torch.empty(n, op["feat"], device=self.device).bernoulli_(keep).div_(keep)
         return torch.empty(n, op["feat"]).bernoulli_(keep).div_(keep)
 
     # ------------------------------------------------------------------ loss head

@@ -37,7 +37,7 @@ extern "C" {
 #define CLB_LOSS_SUM_NLL 1 /* nll_loss(log_softmax, size_average=False)   main_EWC.py:148 */
 #define CLB_LOSS_SUM_SQ 2  /* MSELoss(size_average=False) vs zeros         train_MAS.py:552-560 */
 
-/* GEMM precision modes (clb_set_matmul_mode) */
+/* GEMM precision modes (clb_set_matmul_mode; process default = CLB_MM_TF32X3, or the CLB_MM_MODE environment variable) */
 #define CLB_MM_FP32_SIMT 0 /* exact fp32 FFMA path */
 #define CLB_MM_TF32X3 1    /* tcgen05 kind::tf32, 3-pass split (hi*hi + hi*lo + lo*hi), fp32 accum in TMEM */
 #define CLB_MM_TF32X1 2    /* tcgen05 kind::tf32 single pass (fast, NOT parity mode) */

@@ -18,6 +18,7 @@ from oracle import restate
 from tests.util import rel_err
 
 pytestmark = pytest.mark.gpu
+DEFAULT_MODE = 1      # the library default (CLB_MM_TF32X3); tests that switch modes restore it
 
 
 @pytest.fixture(scope="module")
@@ -131,7 +132,7 @@ def test_conv2d_fwd_bwd(capi, shape, mode):
                   stride, pad, S())
         assert rel_err(dx_, xr.grad) <= tol, "dgrad"
     finally:
-        capi.call("clb_set_matmul_mode", 0)
+        capi.call("clb_set_matmul_mode", DEFAULT_MODE)
 
 
 @pytest.mark.parametrize("M,inf,outf", [(16, 64, 32), (200, 2048, 512), (37, 512, 20), (5, 9216, 4096), (200, 4096, 20)])
@@ -161,7 +162,7 @@ def test_linear_fwd_bwd(capi, M, inf, outf, mode):
         capi.call("clb_linear_dgrad", dyc.data_ptr(), dw.data_ptr(), gx.data_ptr(), ws.data_ptr(), wsb, M, inf, outf, S())
         assert rel_err(gw, wr.grad) <= tol and rel_err(gb, br.grad) <= tol and rel_err(gx, xr.grad) <= tol
     finally:
-        capi.call("clb_set_matmul_mode", 0)
+        capi.call("clb_set_matmul_mode", DEFAULT_MODE)
 
 
 @pytest.mark.parametrize("N,C,H,W,k,s", [(3, 8, 16, 16, 2, 2), (2, 64, 15, 15, 3, 2), (4, 5, 7, 7, 3, 2), (2, 3, 9, 9, 2, 2)])

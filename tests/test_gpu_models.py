@@ -22,6 +22,7 @@ from oracle import restate
 from tests.util import rel_err
 
 pytestmark = pytest.mark.gpu
+DEFAULT_MODE = 1      # the library default (CLB_MM_TF32X3); tests that switch modes restore it
 TOL = 1e-4
 GRAD_TOL = 1e-1      # discontinuity-limited sanity bound, see module docstring
 
@@ -99,7 +100,7 @@ def test_model_step_fisher_mas(name, mode):
             if p.dim() > 1:      # biases start at 0: after two steps they ARE the (discontinuity-limited) gradient
                 assert rel_err(p.data, pr.data) <= GRAD_TOL, ("theta", n)
     finally:
-        _capi.call("clb_set_matmul_mode", 0)
+        _capi.call("clb_set_matmul_mode", DEFAULT_MODE)
 
 
 def test_full_batch_properties_vgg11():
@@ -117,6 +118,7 @@ def test_full_batch_properties_vgg11():
             if hasattr(m, "weight"):
                 m.weight.mul_(10.0)
     eng = Engine(model, (3, 64, 64), 200)
+    _capi.call("clb_set_matmul_mode", 0)                     # (a)/(b) are statements about the exact-fp32 path
     g = torch.Generator().manual_seed(5)
     x = torch.randn(200, 3, 64, 64, generator=g).cuda()
     y = torch.randint(0, 20, (200,), generator=g).cuda()
@@ -135,7 +137,7 @@ def test_full_batch_properties_vgg11():
         for i, (n, _) in enumerate(model.named_parameters()):
             assert rel_err(eng.view(eng.grad, i), eng.view(full, i)) <= GRAD_TOL, n
     finally:
-        _capi.call("clb_set_matmul_mode", 0)
+        _capi.call("clb_set_matmul_mode", DEFAULT_MODE)
     om = torch.zeros_like(full)
     S = torch.cuda.current_stream().cuda_stream
     _capi.call("clb_fisher_accum", om.data_ptr(), full.data_ptr(), 8000.0, om.numel(), S)
@@ -179,4 +181,4 @@ def test_tc_chain_decision_margins(mode):
             for i, ((n, _), gr) in enumerate(zip(ref.named_parameters(), gref)):
                 assert rel_err(eng.view(eng.grad, i), gr) <= tol, (lmode, n)
     finally:
-        _capi.call("clb_set_matmul_mode", 0)
+        _capi.call("clb_set_matmul_mode", DEFAULT_MODE)

@@ -152,3 +152,55 @@ def test_data_parallel_scheme_gloo_world2(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert r.stdout.count("DP_OK") == 2
+
+
+def test_method_plugin_surface():
+    """The Method classes expose what the reference framework reads (src/framework/main.py:109-111,
+    framework_train.py:24,186, lr_grid_train.py:113) and parse()/set_hyperparams() behave like method.py:35-78,238-274."""
+    from clsurvey_b200.methods import method as M
+    for name, cls in (("EWC", M.EWC), ("MAS", M.MAS), ("SI", M.SI), ("GEM", M.GEM), ("finetuning", M.Finetune)):
+        m = M.parse(name)
+        assert isinstance(m, cls) and isinstance(m, M.Method)
+        for attr in ("name", "eval_name", "category", "extra_hyperparams_count", "hyperparams"):
+            assert hasattr(m, attr)
+        assert callable(m.get_output) and callable(m.inference_eval) and callable(m.grid_train)
+    assert M.EWC.hyperparams["lambda"] == 400 and M.MAS.hyperparams["lambda"] == 3 and M.SI.hyperparams["lambda"] == 400
+    assert M.GEM.hyperparams["margin"] == 1 and M.GEM.static_hyperparams["mem_per_task"] == 1024
+    assert M.GEM.wrap_first_task_model and M.Finetune.start_scratch and M.Finetune.no_framework
+    assert M.EWC.category == M.Category.MODEL_BASED and M.GEM.category == M.Category.REHEARSAL_BASED
+    with pytest.raises(NotImplementedError):
+        M.parse("LWF")
+    g = M.GEM()
+    g.hyperparams = type(g.hyperparams)(g.hyperparams)
+    g.static_hyperparams = type(g.static_hyperparams)(g.static_hyperparams)
+    M.set_hyperparams(g, "0.5")
+    M.set_hyperparams(g, "256", static_params=True)
+    assert g.hyperparams["margin"] == 0.5 and g.static_hyperparams["mem_per_task"] == 256.0
+
+
+def test_gem_ring_buffer_host_logic_matches_reference_fixture():
+    """fill_buffer arithmetic (gem.py:322-345) is pure host logic: replay the fixture's key/label stream through the
+    mirror's bookkeeping and compare mem_cnt, labels and exemplar keys bit for bit (no GPU needed)."""
+    from clsurvey_b200.methods.rehearsal.model import common
+    g = load_golden("gem")
+    n_tasks, n_mem = g["n_tasks"], g["n_mem"]
+    mem = common.RehearsalMemory(n_tasks, n_mem, (3, 16, 16))
+    labels = torch.zeros(n_tasks, n_mem, dtype=torch.long)
+    mem_cnt, si = 0, 0
+    for t, (x, y) in enumerate(g["data"]):
+        for b in range(3):
+            st = g["steps"][si]
+            si += 1
+            yb = y[b * 16:(b + 1) * 16]
+            endcnt = min(mem_cnt + yb.size(0), n_mem)
+            eff = endcnt - mem_cnt
+            mem.exemplars[t][mem_cnt:endcnt] = list(st["keys"][:eff])
+            labels[t, mem_cnt:endcnt] = yb[:eff]
+            mem_cnt += eff
+            if mem_cnt == n_mem:
+                mem_cnt = 0
+            assert mem_cnt == st["mem_cnt"]
+    assert torch.equal(labels, g["memory_labels"])
+    for t in range(n_tasks):
+        assert mem[t] == g["exemplars"][t]
+    assert common.compute_offsets(0, [5, 10, 15]) == (0, 5) and common.compute_offsets(2, [5, 10, 15]) == (10, 15)

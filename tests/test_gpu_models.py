@@ -152,11 +152,11 @@ def test_tc_chain_decision_margins(mode):
     tile, W = 4) with seed 37, for which every ReLU pre-activation and every max-pool runner-up is >= 1.8e-4 (relative)
     away from its decision boundary (searched on the CPU), so no unit can flip and gradients are well-posed:
     logits, loss, every parameter gradient, Fisher and MAS omega within 1e-4 of the oracle in fp32 and TF32x3 mode
-    (TF32x1, mode 2, is the non-parity fast mode: 5e-3)."""
+    (TF32x1, mode 2, is the non-parity fast mode: 3e-2)."""
     from clsurvey_b200 import _capi
     from clsurvey_b200.engine import LOSS_MEAN_CE, LOSS_SUM_NLL, LOSS_SUM_SQ, Engine
     from clsurvey_b200.models import VGGSlim
-    tol = 5e-3 if mode == 2 else TOL
+    tol = 3e-2 if mode == 2 else TOL          # mode 2 (single TF32 pass) is the non-parity fast mode: ~1e-3 per layer
     torch.manual_seed(37)
     ref = VGGSlim([32, "M", 32, 64, "M"], 5, 64 * 2 * 2, 32, 32)
     model = copy.deepcopy(ref)

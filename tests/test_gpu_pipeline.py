@@ -118,3 +118,26 @@ def test_cuda_graph_replay_equals_eager(tmp_path, monkeypatch):
     assert out["0"][0] == out["1"][0] and out["0"][1] == out["1"][1]
     for k in out["0"][2]:
         assert torch.equal(out["0"][2][k], out["1"][2][k]), k
+
+
+def test_evaluation_forward_path(tmp_path):
+    """f-1: `test_model` / `get_output_def` (src/framework/inference.py:8-87, method.py:230-235) through the engine:
+    accuracy equals the torch-CPU evaluation of the same model with the same head."""
+    import copy
+    from clsurvey_b200.framework import inference
+    from clsurvey_b200.methods import method as M
+    torch.manual_seed(3)
+    model = tiny_model()
+    with torch.no_grad():
+        for m in model.classifier:
+            if hasattr(m, "weight"):
+                m.weight.mul_(30.0)                      # spread the logits so that arg-max is not degenerate
+    ref = copy.deepcopy(model)
+    ds = {"test": _task(77, 96)}
+    head = copy.deepcopy(model.classifier._modules["4"])
+    acc = inference.test_model(M.EWC(), model, ds, 0, target_head=[head], batch_size=BS, subset="test")
+    ref.eval()
+    x, y = ds["test"].tensors
+    with torch.no_grad():
+        acc_ref = 100.0 * (ref(x).argmax(1) == y).float().mean().item()
+    assert abs(acc - acc_ref) < 1e-9, (acc, acc_ref)

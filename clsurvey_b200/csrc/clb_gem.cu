@@ -259,7 +259,7 @@ static inline int gem_grid(int64_t n_vec, int per_sm) {
 template <int K>
 static int launch_dots_gram(const float* g, const float* G, int64_t ld, int64_t P, const int* idx, double* dots,
                             double* gram, cudaStream_t s) {
-    gem_dots_gram_kernel<K><<<gem_grid(P >> 2, 2), kGemThreads, 0, s>>>(g, G, ld, P, idx, dots, gram); clb::count_launch();
+    gem_dots_gram_kernel<K><<<gem_grid(P >> 2, K <= 2 ? 8 : (K <= 4 ? 4 : 2)), kGemThreads, 0, s>>>(g, G, ld, P, idx, dots, gram); clb::count_launch();
     return 0;
 }
 template <int K>

@@ -196,12 +196,12 @@ def run_gpu_arm(args):
     pk = peaks()
 
     def body(xb, yb):
-        eng.fwd_loss_bwd(xb, yb, denom=GLOBAL_BATCH, train=True)
+        eng.fwd_loss_bwd(xb, yb, denom=GLOBAL_BATCH, train=True, dp_overlap=not args.no_overlap)
         opt.step(model.reg_params)
 
     has_dropout = any(op["kind"] == "dropout" for op in eng.ops)
     eng.dropout_rng = "device"                          # AlexNet: masks drawn on the device (parity tests use host masks)
-    use_graph = (not args.no_graph) and (world == 1 or args.graph_dp) and not has_dropout
+    use_graph = (not args.no_graph) and (world == 1 or not args.no_graph_dp) and not has_dropout
     state = {"run": None}
 
     def step_eager(i):
@@ -250,7 +250,20 @@ def run_gpu_arm(args):
     for i in range(args.warmup):
         step_eager(i)
     if use_graph:
-        state["run"] = eng.graphed(("bench", per), per, body)     # whole step = one CUDA-graph launch
+        ok = 1
+        try:
+            state["run"] = eng.graphed(("bench", per), per, body)     # whole step = one CUDA-graph launch
+        except Exception as e:                                        # e.g. an NCCL build that cannot be captured
+            sys.stderr.write("graph capture failed, running eagerly: %r\n" % (e,))
+            ok = 0
+        if world > 1:                                                 # all ranks replay, or none does
+            import torch.distributed as td
+            flag = torch.tensor([ok], device=dev)
+            td.all_reduce(flag, op=td.ReduceOp.MIN)
+            ok = int(flag.item())
+        if not ok:
+            state["run"] = None
+            eng.drop_graphs()
         for i in range(2):
             step_dev(i)
     sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
@@ -331,6 +344,18 @@ def run_gpu_arm(args):
             "cpu_baseline": cpu,
         }
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    # NCCL keeps a communicator alive while a captured graph still references it: drop the graphs first, and never let
+    # a slow teardown hold the job after the result line is out
+    state["run"] = None
+    eng.drop_graphs()
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    if world > 1:
+        import threading
+        t = threading.Timer(20.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
     cdist.shutdown()
 
 
@@ -344,9 +369,13 @@ def main():
     ap.add_argument("--mm-mode", type=int, default=int(os.environ.get("CLB_MM_MODE", "1")),
                     help="0 exact-fp32 FFMA, 1 tcgen05 TF32x3 (fp32-parity mode, default), 2 tcgen05 TF32x1 (fast, non-parity)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--global-batch", type=int, default=200, help="diagnostics only: the BASELINE workload is 200")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--graph-dp", action="store_true", help="capture the step (incl. the NCCL all-reduce) in a CUDA graph for N > 1")
+    ap.add_argument("--no-graph-dp", action="store_true", help="N > 1: launch eagerly instead of replaying the step (incl. the NCCL all-reduces) as one CUDA graph")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: one all-reduce after backward instead of the overlapped tail/head pair")
     args = ap.parse_args()
+    global GLOBAL_BATCH
+    GLOBAL_BATCH = args.global_batch
     args.warmup = max(args.warmup, 3) if args.impl == "clb" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)

@@ -61,8 +61,10 @@ bool tc_wgrad_supported(int C, int H, int W, int K, int R, int S, int stride, in
 int tc_conv_fwd(const float* x, const float* w2, const float* bias, float* y, int N, int C, int H, int W, int K, int R,
                 int S, int pad, int relu, bool with_lo, cudaStream_t s);
 size_t tc_wgrad_ws_floats(int N, int C, int H, int W, int K, int R, int S);
-int tc_conv_wgrad(const float* x, const float* dy, float* dw, float* ws, int N, int C, int H, int W, int K, int R, int S,
-                  int pad, bool with_lo, cudaStream_t s);
+int tc_conv_wgrad(const float* x, const float* dy, float* dw, float* ws, float* bias_part, bool* bias_partials_done, int N,
+                  int C, int H, int W, int K, int R, int S, int pad, bool with_lo, cudaStream_t s);
+// bias-gradient partial sums fused with the lo-plane split of dY (clb_gemm_simt.cu)
+void conv_bias_partials_and_lo(const float* dy, float* dy_lo, float* scratch, int N, int K, int PQ, cudaStream_t s);
 bool tc3_linear_supported(int M, int in, int out);
 size_t tc3_linear_ws_floats(int M, int in, int out);
 int tc3_linear_fwd(const float* x, const float* w, const float* bias, float* y, float* ws, int M, int in, int out, int relu,

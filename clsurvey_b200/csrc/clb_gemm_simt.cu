@@ -294,8 +294,12 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __rest
 // dbias[k] = sum over (img, pq) of dy[img][k][pq].  Two deterministic stages: grid (K, nsplit) CTAs each reduce a
 // contiguous range of images of one channel (float4 loads, fixed-order tree), then the first nsplit partials are summed
 // in order by the last stage.  No atomics: bit-reproducible.
+// WRITE_LO: the same pass also writes the lo plane (x - trunc19(x)) of dY that the TMA-fed wgrad kernel consumes, so dY
+// is read once for both (the summation order of the bias partials is unchanged).
+template <bool WRITE_LO>
 __global__ void __launch_bounds__(256) conv_bias_grad_partial_kernel(const float* __restrict__ dy, float* __restrict__ part,
-                                                                     int N, int K, int PQ, int imgs_per_split) {
+                                                                     float* __restrict__ dy_lo, int N, int K, int PQ,
+                                                                     int imgs_per_split) {
     const int k = blockIdx.x, sp = blockIdx.y;
     const int n0 = sp * imgs_per_split, n1 = min(N, n0 + imgs_per_split);
     float s = 0.f;
@@ -304,8 +308,17 @@ __global__ void __launch_bounds__(256) conv_bias_grad_partial_kernel(const float
         const int total = (n1 - n0) * pq4;
         for (int i = threadIdx.x; i < total; i += 256) {
             const int img = n0 + i / pq4, q = i - (i / pq4) * pq4;
-            const float4 v = __ldg(reinterpret_cast<const float4*>(dy + ((int64_t)img * K + k) * PQ) + q);
+            const int64_t row = ((int64_t)img * K + k) * PQ;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(dy + row) + q);
             s += (v.x + v.y) + (v.z + v.w);
+            if (WRITE_LO) {
+                float4 o;
+                o.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                o.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                o.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                o.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                reinterpret_cast<float4*>(dy_lo + row)[q] = o;
+            }
         }
     } else {
         const int total = (n1 - n0) * PQ;
@@ -340,7 +353,18 @@ static inline int bias_grad_splits(int N, int K) {
 static void conv_bias_grad(const float* dy, float* db, float* scratch, int N, int K, int PQ, cudaStream_t s) {
     const int want = bias_grad_splits(N, K);
     const int per = (N + want - 1) / want, nsplit = (N + per - 1) / per;
-    conv_bias_grad_partial_kernel<<<dim3(K, nsplit), 256, 0, s>>>(dy, scratch, N, K, PQ, per); clb::count_launch();
+    conv_bias_grad_partial_kernel<false><<<dim3(K, nsplit), 256, 0, s>>>(dy, scratch, nullptr, N, K, PQ, per); clb::count_launch();
+    conv_bias_grad_final_kernel<<<(K + 127) / 128, 128, 0, s>>>(scratch, db, K, nsplit); clb::count_launch();
+}
+// First half of conv_bias_grad fused with the lo-plane split of dY (PQ % 4 == 0); conv_bias_grad_finish() is the rest.
+void conv_bias_partials_and_lo(const float* dy, float* dy_lo, float* scratch, int N, int K, int PQ, cudaStream_t s) {
+    const int want = bias_grad_splits(N, K);
+    const int per = (N + want - 1) / want, nsplit = (N + per - 1) / per;
+    conv_bias_grad_partial_kernel<true><<<dim3(K, nsplit), 256, 0, s>>>(dy, scratch, dy_lo, N, K, PQ, per); clb::count_launch();
+}
+static void conv_bias_grad_finish(const float* scratch, float* db, int N, int K, cudaStream_t s) {
+    const int want = bias_grad_splits(N, K);
+    const int per = (N + want - 1) / want, nsplit = (N + per - 1) / per;
     conv_bias_grad_final_kernel<<<(K + 127) / 128, 128, 0, s>>>(scratch, db, K, nsplit); clb::count_launch();
 }
 
@@ -515,12 +539,15 @@ int clb_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias, f
             set_error("clb_conv2d_wgrad: workspace %zu bytes < required %zu", ws_bytes, tneed);
             return CLB_EWORKSPACE;
         }
-        int rc = tc_conv_wgrad(x, dy, dw, ws, N, C, H, W, K, R, S, pad, mm_mode() == CLB_MM_TF32X3, s);
+        if (dbias && ws_bytes < tneed + (size_t)64 * K * sizeof(float)) { set_error("clb_conv2d_wgrad: workspace too small for bias partials"); return CLB_EWORKSPACE; }
+        float* bias_part = dbias ? ws + tneed / sizeof(float) : nullptr;
+        bool partials_done = false;
+        int rc = tc_conv_wgrad(x, dy, dw, ws, bias_part, &partials_done, N, C, H, W, K, R, S, pad, mm_mode() == CLB_MM_TF32X3, s);
         if (rc) return rc;
         CLB_CHECK_LAUNCH();
         if (dbias) {
-            if (ws_bytes < tneed + (size_t)64 * K * sizeof(float)) { set_error("clb_conv2d_wgrad: workspace too small for bias partials"); return CLB_EWORKSPACE; }
-            conv_bias_grad(dy, dbias, ws + tneed / sizeof(float), N, K, g.P * g.Q, s);
+            if (partials_done) conv_bias_grad_finish(bias_part, dbias, N, K, s);
+            else conv_bias_grad(dy, dbias, bias_part, N, K, g.P * g.Q, s);
             CLB_CHECK_LAUNCH();
         }
         return CLB_OK;

@@ -353,7 +353,7 @@ bool tc3_wgrad_supported(int C, int H, int W, int K, int R, int S, int stride, i
 size_t tc3_wgrad_extra_floats(int N, int C, int H, int W, int K);
 int tc3_conv_fwd(const float* x, const float* w2, const float* w2_lo, const float* bias, float* y, int N, int C, int H, int W,
                  int K, int R, int S, int pad, int relu, bool with_lo, cudaStream_t s);
-int tc3_conv_wgrad(const float* x, const float* dy, float* ws_partials, float* x_lo, float* dy_lo, int N, int C, int H, int W,
+int tc3_conv_wgrad(const float* x, const float* dy, float* ws_partials, float* bias_part, float* dy_lo, int N, int C, int H, int W,
                    int K, int R, int S, int pad, bool with_lo, int splits, int kb_per_split, cudaStream_t s);
 
 // CLB_TC_IMPL: 1 = first generation (both operands gathered into smem), 2 = A through TMEM, 3 (default) = gen-2 plus
@@ -457,8 +457,9 @@ size_t tc_wgrad_ws_floats(int N, int C, int H, int W, int K, int R, int S) {
     return need;
 }
 
-int tc_conv_wgrad(const float* x, const float* dy, float* dw, float* ws, int N, int C, int H, int W, int K, int R, int S,
-                  int pad, bool with_lo, cudaStream_t s) {
+int tc_conv_wgrad(const float* x, const float* dy, float* dw, float* ws, float* bias_part, bool* bias_partials_done, int N,
+                  int C, int H, int W, int K, int R, int S, int pad, bool with_lo, cudaStream_t s) {
+    *bias_partials_done = false;
     using namespace tc;
     const int P = H, Q = W, npix = N * P * Q, n_rows = R * S * C;
     int bn, splits, per;
@@ -466,8 +467,9 @@ int tc_conv_wgrad(const float* x, const float* dy, float* dw, float* ws, int N, 
         tc3_wgrad_plan(N, C, H, W, K, R, S, &splits, &per);
         size_t off = ((size_t)splits * K * n_rows + 7) & ~(size_t)3;              // keep the lo plane 16-byte aligned
         float* dy_lo = ws + off;
-        int rc3 = tc3_conv_wgrad(x, dy, ws, nullptr, dy_lo, N, C, H, W, K, R, S, pad, with_lo, splits, per, s);
+        int rc3 = tc3_conv_wgrad(x, dy, ws, with_lo ? bias_part : nullptr, dy_lo, N, C, H, W, K, R, S, pad, with_lo, splits, per, s);
         if (rc3) return rc3;
+        *bias_partials_done = with_lo && bias_part != nullptr;
         splitk_reduce_permute_kernel<<<ew_blocks((int64_t)K * n_rows), 256, 0, s>>>(ws, dw, K, C, R * S, splits); clb::count_launch();
         return CLB_OK;
     }

@@ -512,11 +512,13 @@ bool tc3_wgrad_supported(int C, int H, int W, int K, int R, int S, int stride, i
 size_t tc3_wgrad_extra_floats(int N, int C, int H, int W, int K) { return (size_t)N * K * H * W + 8; }
 
 // ws layout: [split-K partials] [dy_lo]
-int tc3_conv_wgrad(const float* x, const float* dy, float* ws_partials, float* /*x_lo (unused)*/, float* dy_lo, int N, int C,
+int tc3_conv_wgrad(const float* x, const float* dy, float* ws_partials, float* bias_part, float* dy_lo, int N, int C,
                    int H, int W, int K, int R, int S, int pad, bool with_lo, int splits, int kb_per_split, cudaStream_t s) {
     using namespace tc3;
     const int PQ = H * W, n_rows = R * S * C, npix = N * PQ;
-    if (with_lo) {
+    if (with_lo && bias_part) {
+        clb::conv_bias_partials_and_lo(dy, dy_lo, bias_part, N, K, PQ, s);      // one read of dY for both
+    } else if (with_lo) {
         split_lo_kernel<<<ew_blocks(((int64_t)N * K * PQ) >> 2), 256, 0, s>>>(dy, dy_lo, (int64_t)N * K * PQ); clb::count_launch();
     }
     CUtensorMap m_dy, m_dy_lo;

@@ -57,16 +57,24 @@ def init(backend=None):
         comm = ctypes.c_void_p()
         _capi.call("clb_nccl_init", ctypes.addressof(ident), rk, world, ctypes.addressof(comm))
         _state["comm"] = comm
+        _comm_stream()
 
 
 def shutdown():
     import torch.distributed as td
     if _state["comm"] is not None:
+        # NCCL does not release a communicator while a captured CUDA graph still references it
+        from . import engine as _engine
+        for e in set(_engine._ENGINES.values()):
+            e.drop_graphs()
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
         _capi.call("clb_nccl_destroy", _state["comm"])
         _state["comm"] = None
     if td.is_available() and td.is_initialized():
         td.destroy_process_group()
-    _state.update(world=1, rank=0, backend=None)
+    _state.update(world=1, rank=0, backend=None, stream=None)
 
 
 def shard_rows(n, world=None, rk=None):
@@ -97,10 +105,47 @@ def allreduce_flat(t):
         td.all_reduce(t)
 
 
+def _comm_stream():
+    if _state.get("stream") is None:
+        _state["stream"] = torch.cuda.Stream()
+    return _state["stream"]
+
+
+def start_tail_allreduce(engine, cut):
+    """Called by Engine.backward once every gradient at flat offset >= cut is final: all-reduce grad[cut:] on the
+    communication stream while the compute stream goes on with the backward pass of the first layers.  Both
+    collectives of a step are issued on the communication stream, in the same order on every rank."""
+    main, side = torch.cuda.current_stream(), _comm_stream()
+    ev = torch.cuda.Event()
+    ev.record(main)
+    side.wait_event(ev)
+    tail = engine.grad[cut:]
+    _capi.call("clb_nccl_allreduce_f32", _state["comm"], tail.data_ptr(), tail.numel(), side.cuda_stream)
+    engine.n_launch += 1
+    return cut
+
+
 def allreduce_grads(engine):
-    if _state["world"] > 1:
+    """Sum the flat gradient over ranks.  If backward() already started the tail (dp_overlap), only the head is left:
+    it goes on the communication stream behind the tail, and the compute stream waits for both."""
+    if _state["world"] <= 1:
+        return
+    cut = getattr(engine, "_dp_pending", None)
+    engine._dp_pending = None
+    if not cut:
         allreduce_flat(engine.grad)
         engine.n_launch += 1
+        return
+    main, side = torch.cuda.current_stream(), _comm_stream()
+    ev = torch.cuda.Event()
+    ev.record(main)
+    side.wait_event(ev)
+    head = engine.grad[:cut]
+    _capi.call("clb_nccl_allreduce_f32", _state["comm"], head.data_ptr(), head.numel(), side.cuda_stream)
+    done = torch.cuda.Event()
+    done.record(side)
+    main.wait_event(done)
+    engine.n_launch += 1
 
 
 def allreduce_scalars(vals):

@@ -312,10 +312,32 @@ class Engine:
         self.n_launch += 1
 
     # ------------------------------------------------------------------ backward
-    def backward(self, accumulate=False):
+    def _dp_cut(self):
+        """Data parallelism: (op index, flat offset) at which the gradient buffer is split into a small head (the first
+        layers, <= 10 % of the parameters) and the tail.  backward() produces the tail first, so its all-reduce can run
+        on a side stream underneath the backward pass of the head layers.  (0, 0) = no split."""
+        if getattr(self, "_dp_cut_cache", None) is None:
+            cut = (0, 0)
+            for i, op in enumerate(self.ops):
+                if op["kind"] in ("conv", "linear"):
+                    o = self.offsets[op["w"]]
+                    if 0 < o <= 0.1 * self.total and o % 4 == 0:
+                        cut = (i, o)
+            self._dp_cut_cache = cut
+        return self._dp_cut_cache
+
+    def backward(self, accumulate=False, dp_overlap=False):
         """dlogits -> parameter gradients (flat self.grad).  accumulate=True adds to the existing gradient
-        (GEM memory mini-batches, gem.py:239-256, never zero the grads in between)."""
+        (GEM memory mini-batches, gem.py:239-256, never zero the grads in between).  dp_overlap=True (data-parallel
+        training steps only): the caller promises to call dist.allreduce_grads(self) next; the tail of the flat
+        gradient is then all-reduced on a side stream as soon as its last layer is done."""
         n, s = self._n, _stream()
+        self._dp_pending = None
+        cut_op, cut_off = (0, 0)
+        if dp_overlap and not accumulate:
+            from . import dist as _dist
+            if _dist.is_distributed() and self.grad.is_cuda:
+                cut_op, cut_off = self._dp_cut()
         gdst = self.grad
         if accumulate:
             if self._grad_alt is None:
@@ -327,6 +349,9 @@ class Engine:
         for i in range(len(self.ops) - 1, -1, -1):
             op = self.ops[i]
             k = op["kind"]
+            if cut_off and i == cut_op - 1:
+                from . import dist as _dist
+                self._dp_pending = _dist.start_tail_allreduce(self, cut_off)
             if k == "linear":
                 if op["relu"]:
                     call("clb_relu_bwd", _ptr(d), _ptr(op["out"]), _ptr(d), n * op["outf"], s)
@@ -377,12 +402,24 @@ class Engine:
     def zero_grad(self):
         self.grad.zero_()
 
+    def backward_skip(self, dp_overlap=False):
+        """A rank whose shard of the mini-batch is empty contributes a zero gradient -- through the same sequence of
+        collectives as the ranks that ran backward(dp_overlap=...)."""
+        self.grad.zero_()
+        self._dp_pending = None
+        if dp_overlap:
+            from . import dist as _dist
+            if _dist.is_distributed() and self.grad.is_cuda:
+                _, cut_off = self._dp_cut()
+                if cut_off:
+                    self._dp_pending = _dist.start_tail_allreduce(self, cut_off)
+
     # ------------------------------------------------------------------ composite steps
     def fwd_loss_bwd(self, x, y, mode=LOSS_MEAN_CE, denom=None, train=True, masks=None, col_off=0, ncols=None,
-                     accumulate=False):
+                     accumulate=False, dp_overlap=False):
         self.forward(x, train=train, masks=masks)
         self.loss_head(y, mode, denom, col_off, ncols, want_grad=True)
-        self.backward(accumulate=accumulate)
+        self.backward(accumulate=accumulate, dp_overlap=dp_overlap)
 
     def fwd_loss(self, x, y, mode=LOSS_MEAN_CE, col_off=0, ncols=None):
         self.forward(x, train=False)

@@ -73,10 +73,10 @@ def run_train_model(flavour, model, criterion, optimizer, lr, dset_loaders, dset
     LAST_RUN.update(log)
     world, rk = cdist.world_size(), cdist.rank()
     epoch_acc = 0.0
-    # whole-step CUDA graphs (fwd + loss + bwd + fused update = one graph launch).  Off for data-parallel runs (the
-    # NCCL call stays eager) and for models with active Dropout (host-drawn masks change every step).
+    # whole-step CUDA graphs (fwd + loss + bwd + gradient all-reduces + fused update = one graph launch).  Off for
+    # models with active Dropout (host-drawn masks change every step).
     has_dropout = any(op["kind"] == "dropout" for op in eng.ops)
-    use_graph = os.environ.get("CLB_CUDA_GRAPH", "1") == "1" and world == 1
+    use_graph = os.environ.get("CLB_CUDA_GRAPH", "1") == "1"
     seen = set()
     for epoch in range(start_epoch, num_epochs + 1 if si else num_epochs):
         print("Epoch {}/{}".format(epoch, num_epochs - 1))
@@ -112,7 +112,7 @@ def run_train_model(flavour, model, criterion, optimizer, lr, dset_loaders, dset
                     key = ("train", flavour, hi - lo, B, hyper, lam)
                     if key in seen:                       # an eager step with this configuration has already run
                         def body(xs, ys, _B=B):
-                            eng.fwd_loss_bwd(xs, ys, LOSS_MEAN_CE, denom=_B, train=True)
+                            eng.fwd_loss_bwd(xs, ys, LOSS_MEAN_CE, denom=_B, train=True, dp_overlap=True)
                             optimizer.step() if flavour == "sgd" else optimizer.step(model.reg_params)
                         eng.graphed(key, hi - lo, body)(x, y)
                         graphed = True
@@ -122,14 +122,14 @@ def run_train_model(flavour, model, criterion, optimizer, lr, dset_loaders, dset
                     corr_log[i:i + 1].copy_(eng.correct_dev)
                 elif hi > lo:
                     if phase == "train":
-                        eng.fwd_loss_bwd(x, y, LOSS_MEAN_CE, denom=B, train=True)
+                        eng.fwd_loss_bwd(x, y, LOSS_MEAN_CE, denom=B, train=True, dp_overlap=True)
                     else:
                         eng.forward(x, train=False)
                         eng.loss_head(y, LOSS_MEAN_CE, denom=B, want_grad=False)
                     loss_log[i:i + 1].copy_(eng.loss_dev)
                     corr_log[i:i + 1].copy_(eng.correct_dev)
                 elif phase == "train":
-                    eng.zero_grad()
+                    eng.backward_skip(dp_overlap=True)
                 if phase == "train" and not graphed:
                     if flavour == "sgd":
                         optimizer.step()

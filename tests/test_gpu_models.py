@@ -182,3 +182,20 @@ def test_tc_chain_decision_margins(mode):
                 assert rel_err(eng.view(eng.grad, i), gr) <= tol, (lmode, n)
     finally:
         _capi.call("clb_set_matmul_mode", DEFAULT_MODE)
+
+
+def test_dp_gradient_cut_points():
+    """The data-parallel head/tail split of the flat gradient (Engine._dp_cut): head = leading layers with <= 10 % of
+    the parameters, cut on a layer boundary, 16-byte aligned; the tail must be complete when backward reaches the cut."""
+    from clsurvey_b200.engine import Engine
+    for name, make in _models().items():
+        m = make()
+        eng = Engine(m, (3, 64, 64), 8)
+        i, off = eng._dp_cut()
+        assert off % 4 == 0 and off <= 0.1 * eng.total
+        if off:
+            assert eng.ops[i]["kind"] in ("conv", "linear") and eng.offsets[eng.ops[i]["w"]] == off
+            assert all(eng.offsets[op["w"]] < off for op in eng.ops[:i] if op["kind"] in ("conv", "linear"))
+            assert all(eng.offsets[op["w"]] >= off for op in eng.ops[i:] if op["kind"] in ("conv", "linear"))
+        if name == "VGG11":                      # conv1-4 = 1728+64 + 73728+128 + 294912+256 + 589824+256
+            assert off == 960896 and eng.ops[i]["C"] == 256 and eng.ops[i]["K"] == 512

@@ -56,7 +56,10 @@ constexpr int kTile = BM * 128;                     // 16 KB: 128 rows x 128 B
 constexpr int kFwGroups = 4;
 constexpr int kFwWarpTma = 4 * kFwGroups, kFwWarpMma = kFwWarpTma + 1;
 constexpr int kFwThreads = (kFwWarpMma + 1) * 32;     // 576
-constexpr int kFwStagesA = 4, kFwStagesB = 4;
+#ifndef CLB_FW_STAGES_B
+#define CLB_FW_STAGES_B 4
+#endif
+constexpr int kFwStagesA = 4, kFwStagesB = CLB_FW_STAGES_B;
 
 template <int BN, bool WITH_LO> struct FwLayout {
     static constexpr int kBTile = BN * 128;
@@ -107,7 +110,12 @@ fwd_tma_kernel(ALoad A, const __grid_constant__ CUtensorMap map_w, const __grid_
         const typename ALoad::Ctx actx = A.prep(m0 + tg);
         for (int i = group; i < nkb; i += kFwGroups) {
             float v[BK];
+#ifdef CLB_DIAG_NO_A_LOAD                       // timing experiments only (results are garbage)
+#pragma unroll
+            for (int j = 0; j < BK; ++j) v[j] = (float)(i + j + tg);
+#else
             A.row(i, actx, v);
+#endif
             const int s = i % kFwStagesA;
             mbar_wait(a_empty + 8 * s, (((uint32_t)(i / kFwStagesA)) & 1u) ^ 1u);
             tc_fence_after();
@@ -134,10 +142,14 @@ fwd_tma_kernel(ALoad A, const __grid_constant__ CUtensorMap map_w, const __grid_
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % kFwStagesB;
                 mbar_wait(b_empty + 8 * s, (((uint32_t)(i / kFwStagesB)) & 1u) ^ 1u);
+#ifdef CLB_DIAG_NO_B_TMA
+                mbar_arrive(b_full + 8 * s);
+#else
                 tma::mbar_arrive_expect_tx(b_full + 8 * s, (uint32_t)L::kStageB);
                 const uint32_t st = base + (uint32_t)s * L::kStageB;
                 tma::load_2d(st, &map_w, b_full + 8 * s, i * BK, n0);
                 if (WITH_LO) tma::load_2d(st + L::kBTile, &map_w_lo, b_full + 8 * s, i * BK, n0);
+#endif
             }
         }
     } else if (lane == 0) {
@@ -150,6 +162,7 @@ fwd_tma_kernel(ALoad A, const __grid_constant__ CUtensorMap map_w, const __grid_
             const uint32_t st = base + (uint32_t)sb * L::kStageB;
             const uint64_t b_hi = make_desc(st), b_lo = make_desc(st + L::kBTile);
             const uint32_t a_hi = tmem_a0 + (uint32_t)sa * L::kAStageCols, a_lo = a_hi + 32;
+#ifndef CLB_DIAG_NO_MMA
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k) {
                 if (WITH_LO) {
@@ -158,6 +171,7 @@ fwd_tma_kernel(ALoad A, const __grid_constant__ CUtensorMap map_w, const __grid_
                 }
                 umma_tf32_ts(tmem, a_hi + 8 * k, b_hi + 2 * k, idesc, (i | k) != 0);
             }
+#endif
             umma_commit(a_empty + 8 * sa);
             umma_commit(b_empty + 8 * sb);
         }

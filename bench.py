@@ -316,11 +316,12 @@ def run_gpu_arm(args):
 
     if rank == 0:
         conv_tf = conv_f * per / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-        mode_name = {0: "fp32 FFMA (SIMT)", 1: "tf32x3 tcgen05", 2: "tf32x1 tcgen05"}[args.mm_mode]
+        mode_name = {0: "fp32 FFMA (SIMT)", 1: "tf32x3 tcgen05", 2: "tf32x1 tcgen05",
+                     3: "bf16x3 tcgen05 (conv fwd/dgrad) + tf32x3"}[args.mm_mode]
         line = {
             "metric": "images/sec/task", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32" if args.mm_mode == 0 else "tf32x3->f32",
+            "vs_baseline": None, "dtype": {0: "f32", 1: "tf32x3->f32", 2: "tf32", 3: "bf16x3/tf32x3->f32"}[args.mm_mode],
             "data": "synthetic",
             "config": {"workload": "%s bs=%d MAS-style penalised SGD step, 64x64 inputs (BASELINE configs[2])" % (
                 args.model, GLOBAL_BATCH), "global_batch": GLOBAL_BATCH, "per_gpu_batch": per,

@@ -12,6 +12,8 @@ namespace clb {
 void set_error(const char* fmt, ...);
 int sm_count();
 int mm_mode();
+// modes that keep fp32 parity through an operand split (the lo planes are needed)
+inline bool mm_split() { return mm_mode() == CLB_MM_TF32X3 || mm_mode() == CLB_MM_BF16X3; }
 void count_launch();      // every kernel launch of this library is counted (bench.py's gpu_launches)
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -71,7 +73,16 @@ int tc3_linear_fwd(const float* x, const float* w, const float* bias, float* y, 
                    bool with_lo, cudaStream_t s);
 int tc3_linear_dgrad(const float* dy, const float* w, float* dx, float* ws, int M, int in, int out, bool with_lo, cudaStream_t s);
 int tc3_linear_wgrad(const float* x, const float* dy, float* dw, float* ws, int M, int in, int out, bool with_lo, cudaStream_t s);
-void tc_permute_w_fwd(const float* w, float* w2, int K, int C, int RS, cudaStream_t s);
-void tc_permute_w_dgrad(const float* w, float* wd, int K, int C, int R, int S, cudaStream_t s);
+void tc_permute_w_fwd(const float* w, float* w2, int K, int C, int RS, cudaStream_t s, bool bf16 = false);
+void tc_permute_w_dgrad(const float* w, float* wd, int K, int C, int R, int S, cudaStream_t s, bool bf16 = false);
+// bf16 hi/lo split kernels for conv fwd / dgrad (clb_gemm_tc4.cu); the bf16 planes sit where the fp32 planes would
+bool tc4_fwd_supported(int C);
+bool tc_bf16_route(int reduction_channels);      // mode == CLB_MM_BF16X3 and the bf16 kernel can take this layer
+int tc_conv_fwd_bf16(const float* x, const float* w, float* w_ws, const float* bias, float* y, int N, int C, int H, int W, int K,
+                     int R, int S, int pad, int relu, cudaStream_t s);
+int tc_conv_dgrad_bf16(const float* dy, const float* w, float* wt_ws, float* dx, int N, int C, int P, int Q, int K, int R, int S,
+                       int pad, cudaStream_t s);
+int tc4_conv_fwd(const float* x, const void* w_hi, const void* w_lo, const float* bias, float* y, int N, int C, int H, int W,
+                 int K, int R, int S, int pad, int relu, cudaStream_t s);
 
 }  // namespace clb

@@ -6,7 +6,7 @@
 
 namespace clb {
 static thread_local char g_err[512] = "";
-// default: tensor-core parity mode (3-pass TF32 split); CLB_MM_MODE=0/1/2 overrides at first use
+// default: tensor-core parity mode (3-pass TF32 split); CLB_MM_MODE=0/1/2/3 overrides at first use
 static int g_mm_mode = -1;
 
 void set_error(const char* fmt, ...) {
@@ -31,7 +31,7 @@ int sm_count() {
 int mm_mode() {
     if (g_mm_mode < 0) {
         const char* e = getenv("CLB_MM_MODE");
-        g_mm_mode = (e && e[0] >= '0' && e[0] <= '2' && e[1] == 0) ? (e[0] - '0') : CLB_MM_TF32X3;
+        g_mm_mode = (e && e[0] >= '0' && e[0] <= '3' && e[1] == 0) ? (e[0] - '0') : CLB_MM_TF32X3;
     }
     return g_mm_mode;
 }
@@ -52,7 +52,7 @@ int clb_sm_count(int* out) {
     return CLB_OK;
 }
 int clb_set_matmul_mode(int mode) {
-    CLB_CHECK_ARG(mode == CLB_MM_FP32_SIMT || mode == CLB_MM_TF32X3 || mode == CLB_MM_TF32X1);
+    CLB_CHECK_ARG(mode == CLB_MM_FP32_SIMT || mode == CLB_MM_TF32X3 || mode == CLB_MM_TF32X1 || mode == CLB_MM_BF16X3);
     clb::g_mm_mode = mode;
     return CLB_OK;
 }

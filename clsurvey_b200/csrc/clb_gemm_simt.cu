@@ -471,8 +471,14 @@ int clb_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, 
     CLB_CHECK_ARG((int64_t)N * C * H * W < (1LL << 31) && (int64_t)N * K * H * W < (1LL << 31));
     ConvGeom g = make_geom(N, C, H, W, K, R, S, stride, pad);
     if (mm_mode() != CLB_MM_FP32_SIMT && w_ws != nullptr && tc_fwd_supported(C, H, W, K, R, S, stride, pad)) {
+        if (tc_bf16_route(C)) {
+            int rc4 = tc_conv_fwd_bf16(x, w, w_ws, bias, y, N, C, H, W, K, R, S, pad, relu, as_stream(stream));
+            if (rc4) return rc4;
+            CLB_CHECK_LAUNCH();
+            return CLB_OK;
+        }
         tc_permute_w_fwd(w, w_ws, K, C, R * S, as_stream(stream));           // [K][C][RS] -> [K][RS][C]
-        int rc = tc_conv_fwd(x, w_ws, bias, y, N, C, H, W, K, R, S, pad, relu, mm_mode() == CLB_MM_TF32X3, as_stream(stream));
+        int rc = tc_conv_fwd(x, w_ws, bias, y, N, C, H, W, K, R, S, pad, relu, mm_split(), as_stream(stream));
         if (rc) return rc;
         CLB_CHECK_LAUNCH();
         return CLB_OK;
@@ -488,8 +494,14 @@ int clb_conv2d_dgrad(const float* dy, const float* w, float* dx, float* wt_ws, i
     cudaStream_t s = as_stream(stream);
     ConvGeom g = make_geom(N, C, H, W, K, R, S, stride, pad);
     if (mm_mode() != CLB_MM_FP32_SIMT && wt_ws != nullptr && tc_dgrad_supported(C, H, W, K, R, S, stride, pad)) {
+        if (tc_bf16_route(K)) {
+            int rc4 = tc_conv_dgrad_bf16(dy, w, wt_ws, dx, N, C, g.P, g.Q, K, R, S, pad, s);
+            if (rc4) return rc4;
+            CLB_CHECK_LAUNCH();
+            return CLB_OK;
+        }
         tc_permute_w_dgrad(w, wt_ws, K, C, R, S, s);                          // [K][C][R][S] -> [C][flipped RS][K]
-        int rc = tc_conv_fwd(dy, wt_ws, nullptr, dx, N, K, g.P, g.Q, C, R, S, R - 1 - pad, 0, mm_mode() == CLB_MM_TF32X3, s);
+        int rc = tc_conv_fwd(dy, wt_ws, nullptr, dx, N, K, g.P, g.Q, C, R, S, R - 1 - pad, 0, mm_split(), s);
         if (rc) return rc;
         CLB_CHECK_LAUNCH();
         return CLB_OK;
@@ -542,7 +554,7 @@ int clb_conv2d_wgrad(const float* x, const float* dy, float* dw, float* dbias, f
         if (dbias && ws_bytes < tneed + (size_t)64 * K * sizeof(float)) { set_error("clb_conv2d_wgrad: workspace too small for bias partials"); return CLB_EWORKSPACE; }
         float* bias_part = dbias ? ws + tneed / sizeof(float) : nullptr;
         bool partials_done = false;
-        int rc = tc_conv_wgrad(x, dy, dw, ws, bias_part, &partials_done, N, C, H, W, K, R, S, pad, mm_mode() == CLB_MM_TF32X3, s);
+        int rc = tc_conv_wgrad(x, dy, dw, ws, bias_part, &partials_done, N, C, H, W, K, R, S, pad, mm_split(), s);
         if (rc) return rc;
         CLB_CHECK_LAUNCH();
         if (dbias) {
@@ -602,7 +614,7 @@ int clb_linear_fwd(const float* x, const float* w, const float* bias, float* y, 
     CLB_CHECK_ARG(x && w && y && M > 0 && in > 0 && out > 0);
     cudaStream_t s = as_stream(stream);
     if (linear_on_tc(ws, ws_bytes, M, in, out)) {
-        int rc = tc3_linear_fwd(x, w, bias, y, ws, M, in, out, relu, mm_mode() == CLB_MM_TF32X3, s);
+        int rc = tc3_linear_fwd(x, w, bias, y, ws, M, in, out, relu, mm_split(), s);
         if (rc) return rc;
         CLB_CHECK_LAUNCH();
         return CLB_OK;
@@ -626,7 +638,7 @@ int clb_linear_dgrad(const float* dy, const float* w, float* dx, float* ws, size
     CLB_CHECK_ARG(dy && w && dx && M > 0 && in > 0 && out > 0);
     cudaStream_t s = as_stream(stream);
     if (linear_on_tc(ws, ws_bytes, M, in, out)) {
-        int rc = tc3_linear_dgrad(dy, w, dx, ws, M, in, out, mm_mode() == CLB_MM_TF32X3, s);
+        int rc = tc3_linear_dgrad(dy, w, dx, ws, M, in, out, mm_split(), s);
         if (rc) return rc;
         CLB_CHECK_LAUNCH();
         return CLB_OK;
@@ -645,7 +657,7 @@ int clb_linear_wgrad(const float* x, const float* dy, float* dw, float* dbias, f
     CLB_CHECK_ARG(x && dy && dw && M > 0 && in > 0 && out > 0);
     cudaStream_t s = as_stream(stream);
     if (linear_on_tc(ws, ws_bytes, M, in, out)) {
-        int rc = tc3_linear_wgrad(x, dy, dw, ws, M, in, out, mm_mode() == CLB_MM_TF32X3, s);
+        int rc = tc3_linear_wgrad(x, dy, dw, ws, M, in, out, mm_split(), s);
         if (rc) return rc;
         CLB_CHECK_LAUNCH();
         if (dbias) {

@@ -281,25 +281,37 @@ gemm_tc_kernel(ALoad A, BLoad B, Epi epi, int num_kb_total, int kb_per_split) {
 
 // ---------------------------------------------------------------------------------------------- helper kernels
 // w[K][C][RS] -> w2[K][ld] with w2[k][rs*C + c]   (forward GEMM-B, K order (r,s,c)); ld > RS*C zero-pads the row
+// bf16 planes (mode CLB_MM_BF16X3): hi = bf16_rn(v), lo = bf16_rn(v - hi), stored as 16-bit arrays in the same workspace
+__device__ __forceinline__ void store_bf16_split(float v, float* hi_plane, float* lo_plane, int64_t i) {
+    uint32_t u = __float_as_uint(v);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    const uint32_t h = u >> 16;
+    uint32_t r = __float_as_uint(v - __uint_as_float(h << 16));
+    r += 0x7FFFu + ((r >> 16) & 1u);
+    reinterpret_cast<uint16_t*>(hi_plane)[i] = (uint16_t)h;
+    reinterpret_cast<uint16_t*>(lo_plane)[i] = (uint16_t)(r >> 16);
+}
 __global__ void permute_w_fwd_kernel(const float* __restrict__ w, float* __restrict__ w2, float* __restrict__ w2_lo, int K,
-                                     int C, int RS, int ld) {
+                                     int C, int RS, int ld, int bf16) {
     const int64_t total = (int64_t)K * ld, gs = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gs) {
         const int j = (int)(i % ld), k = (int)(i / ld);
         const int c = j % C, rs = j / C;
         const float v = (j < RS * C) ? w[((int64_t)k * C + c) * RS + rs] : 0.f;
+        if (bf16) { store_bf16_split(v, w2, w2_lo, i); continue; }
         w2[i] = v;
         if (w2_lo) w2_lo[i] = v - __uint_as_float(__float_as_uint(v) & kHiMask);     // TMA-fed kernels read the lo plane
     }
 }
 // w[K][C][R][S] -> wd[C][(R-1-r, S-1-s)][K]   (dgrad = forward conv of dY: rows = c, K order (r', s', kout))
 __global__ void permute_w_dgrad_kernel(const float* __restrict__ w, float* __restrict__ wd, float* __restrict__ wd_lo, int K,
-                                       int C, int R, int S) {
+                                       int C, int R, int S, int bf16) {
     const int64_t total = (int64_t)K * C * R * S, gs = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gs) {
         const int k = (int)(i % K), rs = (int)((i / K) % (R * S)), c = (int)(i / ((int64_t)K * R * S));
         const int r = R - 1 - rs / S, s = S - 1 - rs % S;
         const float v = w[(((int64_t)k * C + c) * R + r) * S + s];
+        if (bf16) { store_bf16_split(v, wd, wd_lo, i); continue; }
         wd[i] = v;
         if (wd_lo) wd_lo[i] = v - __uint_as_float(__float_as_uint(v) & kHiMask);
     }
@@ -501,14 +513,28 @@ size_t tc_w_plane_floats(int K, int C, int R, int S) {
     m = m > c ? m : c;
     return (m + 3) & ~(size_t)3;
 }
-void tc_permute_w_fwd(const float* w, float* w2, int K, int C, int RS, cudaStream_t s) {
-    const int ld = (C % 32 == 0) ? RS * C : 32;
-    float* lo = tc_impl() >= 3 ? w2 + tc_w_plane_floats(K, C, RS, 1) : nullptr;
-    tc::permute_w_fwd_kernel<<<tc::ew_blocks((int64_t)K * ld), 256, 0, s>>>(w, w2, lo, K, C, RS, ld); clb::count_launch();
+bool tc_bf16_route(int reduction_channels) {
+    return mm_mode() == CLB_MM_BF16X3 && tc_impl() >= 3 && tc4_fwd_supported(reduction_channels);
 }
-void tc_permute_w_dgrad(const float* w, float* wd, int K, int C, int R, int S, cudaStream_t s) {
-    float* lo = tc_impl() >= 3 ? wd + tc_w_plane_floats(K, C, R, S) : nullptr;
-    tc::permute_w_dgrad_kernel<<<tc::ew_blocks((int64_t)K * C * R * S), 256, 0, s>>>(w, wd, lo, K, C, R, S); clb::count_launch();
+int tc_conv_fwd_bf16(const float* x, const float* w, float* w_ws, const float* bias, float* y, int N, int C, int H, int W, int K,
+                     int R, int S, int pad, int relu, cudaStream_t s) {
+    tc_permute_w_fwd(w, w_ws, K, C, R * S, s, true);                           // [K][C][RS] -> bf16 hi / lo planes [K][RS][C]
+    return tc4_conv_fwd(x, w_ws, w_ws + tc_w_plane_floats(K, C, R, S), bias, y, N, C, H, W, K, R, S, pad, relu, s);
+}
+// dgrad = forward conv of dY [N, K, P, Q] with the flipped / transposed filters, output [N, C, P, Q] (stride 1, same size)
+int tc_conv_dgrad_bf16(const float* dy, const float* w, float* wt_ws, float* dx, int N, int C, int P, int Q, int K, int R, int S,
+                       int pad, cudaStream_t s) {
+    tc_permute_w_dgrad(w, wt_ws, K, C, R, S, s, true);                         // -> bf16 planes [C][flipped RS][K]
+    return tc4_conv_fwd(dy, wt_ws, wt_ws + tc_w_plane_floats(K, C, R, S), nullptr, dx, N, K, P, Q, C, R, S, R - 1 - pad, 0, s);
+}
+void tc_permute_w_fwd(const float* w, float* w2, int K, int C, int RS, cudaStream_t s, bool bf16) {
+    const int ld = (C % 32 == 0) ? RS * C : 32;
+    float* lo = (tc_impl() >= 3 || bf16) ? w2 + tc_w_plane_floats(K, C, RS, 1) : nullptr;
+    tc::permute_w_fwd_kernel<<<tc::ew_blocks((int64_t)K * ld), 256, 0, s>>>(w, w2, lo, K, C, RS, ld, bf16 ? 1 : 0); clb::count_launch();
+}
+void tc_permute_w_dgrad(const float* w, float* wd, int K, int C, int R, int S, cudaStream_t s, bool bf16) {
+    float* lo = (tc_impl() >= 3 || bf16) ? wd + tc_w_plane_floats(K, C, R, S) : nullptr;
+    tc::permute_w_dgrad_kernel<<<tc::ew_blocks((int64_t)K * C * R * S), 256, 0, s>>>(w, wd, lo, K, C, R, S, bf16 ? 1 : 0); clb::count_launch();
 }
 
 }  // namespace clb

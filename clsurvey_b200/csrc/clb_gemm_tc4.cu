@@ -1,0 +1,220 @@
+// tcgen05 implicit-GEMM, bf16 hi/lo split ("bf16x3") for conv forward / dgrad: mode CLB_MM_BF16X3.
+//
+// Why: profiles/README.md "Where the conv time goes" -- in the TF32x3 parity mode the forward/dgrad kernel is bound by
+// the tensor pipe itself (3 x the algorithmic flops at the TF32 rate).  kind::f16 with bf16 operands runs K = 16 per MMA
+// at twice the TF32 rate and moves half the operand bytes.  x = hi + lo with hi = bf16_rn(x), lo = bf16_rn(x - hi)
+// leaves a residual <= 2^-18 |x|; the three products hi*hi + hi*lo + lo*hi (fp32 accumulation in TMEM, cross terms in
+// their own accumulator like the TF32 kernels) give ~1e-5 relative error per dot product -- inside the 1e-4 budget of
+// north_star, but ~8x coarser per operand than the TF32 split, hence a separate, opt-in mode.
+// Operand conventions pinned on the GPU by tools/bf16_probe.py (profiles/r1_bf16_probe.log):
+//   * smem operand: K-major rows of 64 bf16 = one 128-byte swizzled row (same descriptor as the tf32 tiles; one MMA
+//     advances the descriptor by 32 bytes = 16 bf16);
+//   * TMEM operand: 32-bit cells holding two consecutive K elements, even k in the low half, 8 cells per MMA,
+//     written with tcgen05.st.32x32b (lane = GEMM row).
+// Structure = tc3::fwd_tma_kernel: 4 gather groups (one GEMM row per thread, 64 K elements per K block, converted to
+// hi/lo cell pairs in registers -> TMEM), weight tiles (hi and lo bf16 planes written by the permute kernels) by TMA,
+// one MMA-issuing thread, epilogue by warps 0-7.
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include "clb_tc_loaders.cuh"
+#include "clb_tma.cuh"
+
+namespace clb {
+namespace tc4 {
+using namespace clb::tc;
+using clb::tcl::EpiNCHW;
+using clb::tcl::PixelRows;
+using clb::tcl::tmem_st32;
+using clb::tcl::tmem_wait_st;
+
+constexpr int kGroups = 4;
+constexpr int kWarpTma = 4 * kGroups, kWarpMma = kWarpTma + 1;
+constexpr int kThreads = (kWarpMma + 1) * 32;          // 576
+constexpr int kStagesA = 4, kStagesB = 4;
+constexpr int BK2 = 64;                                // K elements per K block (one 128-byte row of bf16)
+static_assert(kGroups == kStagesA, "group g must own TMEM stage g (parity waits stay within one phase)");
+
+template <int BN> struct Layout {
+    static constexpr int kBTile = BN * 128;            // BN rows x 64 bf16
+    static constexpr int kStageB = 2 * kBTile;         // hi + lo
+    static constexpr int kBarOff = kStageB * kStagesB;
+    static constexpr int kTotal = kBarOff + 256 + 1024;
+    static constexpr int kAccCols = 2 * BN;            // main + cross-term accumulator
+    static constexpr int kAStageCols = 64;             // 32 hi cells + 32 lo cells
+    static constexpr int kColsNeeded = kAccCols + kStagesA * kAStageCols;
+    static constexpr int kTmemCols = 512;
+    static_assert(kColsNeeded <= 512, "TMEM budget");
+};
+
+// instruction descriptor for kind::f16: D = F32, A = B = BF16, K-major both, N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// (v0, v1) -> hi cell (bf16_rn(v0) | bf16_rn(v1) << 16) and lo cell of the residuals
+__device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);                     // .x = v0 -> low half
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float r0 = v0 - __uint_as_float(hi << 16), r1 = v1 - __uint_as_float(hi & 0xFFFF0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+template <int BN, class ALoad, class Epi>
+__global__ void __launch_bounds__(kThreads, 1)
+fwd_bf16_kernel(ALoad A, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_w_lo, Epi epi, int nkb) {
+    using L = Layout<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar = base + L::kBarOff;
+    const uint32_t a_full = bar, a_empty = bar + 8 * kStagesA;
+    const uint32_t b_full = bar + 16 * kStagesA, b_empty = b_full + 8 * kStagesB;
+    const uint32_t bar_tmem = b_empty + 8 * kStagesB, slot = bar_tmem + 8;
+    uint32_t* slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (slot - smem_u32(smem_raw)));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStagesA; ++s) { mbar_init(a_full + 8 * s, 4); mbar_init(a_empty + 8 * s, 1); }
+        for (int s = 0; s < kStagesB; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
+        mbar_init(bar_tmem, 1);
+        fence_barrier_init();
+        tma::prefetch_desc(&map_w);
+        tma::prefetch_desc(&map_w_lo);
+    }
+    if (warp == kWarpMma) tmem_alloc(slot, L::kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *slot_ptr;
+    const uint32_t tmem_a0 = tmem + L::kAccCols;
+
+    if (warp < kWarpTma) {
+        const int group = warp >> 2, tg = threadIdx.x & 127;
+        const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
+        const typename ALoad::Ctx actx = A.prep(m0 + tg);
+        for (int i = group; i < nkb; i += kGroups) {
+            float v0[BK], v1[BK];                                  // the two 32-element halves of this 64-element K block
+            A.row(2 * i, actx, v0);
+            A.row(2 * i + 1, actx, v1);
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                split_pair(v0[2 * j], v0[2 * j + 1], hi[j], lo[j]);
+                split_pair(v1[2 * j], v1[2 * j + 1], hi[16 + j], lo[16 + j]);
+            }
+            const int s = i % kStagesA;
+            mbar_wait(a_empty + 8 * s, (((uint32_t)(i / kStagesA)) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t col = tmem_a0 + (uint32_t)s * L::kAStageCols;
+            tmem_st32(lane_field + col, hi);
+            tmem_st32(lane_field + col + 32, lo);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full + 8 * s);
+        }
+    } else if (warp == kWarpTma) {
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % kStagesB;
+                mbar_wait(b_empty + 8 * s, (((uint32_t)(i / kStagesB)) & 1u) ^ 1u);
+                tma::mbar_arrive_expect_tx(b_full + 8 * s, (uint32_t)L::kStageB);
+                const uint32_t st = base + (uint32_t)s * L::kStageB;
+                tma::load_2d(st, &map_w, b_full + 8 * s, i * BK2, n0);
+                tma::load_2d(st + L::kBTile, &map_w_lo, b_full + 8 * s, i * BK2, n0);
+            }
+        }
+    } else if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(BN);
+        for (int i = 0; i < nkb; ++i) {
+            const int sa = i % kStagesA, sb = i % kStagesB;
+            mbar_wait(a_full + 8 * sa, ((uint32_t)(i / kStagesA)) & 1u);
+            mbar_wait(b_full + 8 * sb, ((uint32_t)(i / kStagesB)) & 1u);
+            tc_fence_after();
+            const uint32_t st = base + (uint32_t)sb * L::kStageB;
+            const uint64_t b_hi = make_desc(st), b_lo = make_desc(st + L::kBTile);
+            const uint32_t a_hi = tmem_a0 + (uint32_t)sa * L::kAStageCols, a_lo = a_hi + 32;
+#pragma unroll
+            for (int k = 0; k < BK2 / 16; ++k) {
+                umma_bf16_ts(tmem + BN, a_lo + 8 * k, b_hi + 2 * k, idesc, (i | k) != 0);
+                umma_bf16_ts(tmem + BN, a_hi + 8 * k, b_lo + 2 * k, idesc, 1);
+                umma_bf16_ts(tmem, a_hi + 8 * k, b_hi + 2 * k, idesc, (i | k) != 0);
+            }
+            umma_commit(a_empty + 8 * sa);
+            umma_commit(b_empty + 8 * sb);
+        }
+        umma_commit(bar_tmem);
+    }
+
+    if (warp < 8) {
+        if (nkb > 0) {
+            mbar_wait(bar_tmem, 0);
+            tc_fence_after();
+        }
+        const int lane_grp = warp & 3, col_half = warp >> 2;
+        const int m = m0 + lane_grp * 32 + lane;
+#pragma unroll 1
+        for (int c = 0; c < BN / 2; c += 16) {
+            const int col = col_half * (BN / 2) + c;
+            uint32_t r[16], r2[16];
+            tmem_ld16(tmem + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)col, r);
+            tmem_ld16(tmem + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(BN + col), r2);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+            epi.store16(m, n0 + col, r, 0);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kWarpMma) tmem_dealloc(tmem, L::kTmemCols);
+}
+
+template <int BN, class ALoad>
+static int launch_fwd(const ALoad& A, const uint16_t* w_hi, const uint16_t* w_lo, int n_rows, int ld, const EpiNCHW& e, int M,
+                      int nkb, cudaStream_t s) {
+    using L = Layout<BN>;
+    CUtensorMap mw, mwl;
+    const uint64_t dims[2] = {(uint64_t)ld, (uint64_t)n_rows};
+    const uint64_t str[1] = {(uint64_t)ld * 2};
+    const uint32_t box[2] = {(uint32_t)BK2, (uint32_t)BN};
+    int rc = tma::encode_bf16(&mw, w_hi, 2, dims, str, box, true);
+    if (rc) return rc;
+    rc = tma::encode_bf16(&mwl, w_lo, 2, dims, str, box, true);
+    if (rc) return rc;
+    auto kern = fwd_bf16_kernel<BN, ALoad, EpiNCHW>;
+    static bool configured = false;
+    if (!configured) { CLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal)); configured = true; }
+    dim3 grid((M + BM - 1) / BM, (n_rows + BN - 1) / BN, 1);
+    kern<<<grid, kThreads, L::kTotal, s>>>(A, mw, mwl, e, nkb); clb::count_launch();
+    return CLB_OK;
+}
+
+}  // namespace tc4
+
+// C = reduction channels of the conv seen as forward (C_in for fwd, K_out for dgrad): whole 64-element K blocks per tap
+bool tc4_fwd_supported(int C) { return (C % 64) == 0; }
+
+// w_hi / w_lo: re-ordered weights [K][R*S*C] as bf16 planes (tc_permute_w_* with bf16 = true)
+int tc4_conv_fwd(const float* x, const void* w_hi, const void* w_lo, const float* bias, float* y, int N, int C, int H, int W,
+                 int K, int R, int S, int pad, int relu, cudaStream_t s) {
+    using namespace tc4;
+    const int P = H, Q = W, M = N * P * Q;
+    EpiNCHW e{y, bias, relu, M, K, P * Q, FastDiv32(P * Q)};
+    PixelRows A{x, C, H, W, R, S, pad, P, Q, M, FastDiv32(P * Q), FastDiv32(Q), FastDiv32(C), FastDiv32(S)};
+    const int ld = R * S * C, nkb = ld / BK2;
+    const uint16_t* wh = static_cast<const uint16_t*>(w_hi);
+    const uint16_t* wl = static_cast<const uint16_t*>(w_lo);
+    if (K % 128 == 0 || K > 64) return launch_fwd<128>(A, wh, wl, K, ld, e, M, nkb, s);
+    return launch_fwd<64>(A, wh, wl, K, ld, e, M, nkb, s);
+}
+
+}  // namespace clb

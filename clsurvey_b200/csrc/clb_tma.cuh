@@ -12,6 +12,9 @@ namespace tma {
 // (stride of dim 1.. in bytes; dim 0 is contiguous).  128-byte swizzle, zero fill out of bounds.
 int encode_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                const uint32_t* box, bool swizzle128);
+// same for a bf16 tensor (dims in elements, strides in bytes)
+int encode_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                const uint32_t* box, bool swizzle128);
 
 __device__ __forceinline__ void prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -41,6 +41,8 @@ extern "C" {
 #define CLB_MM_FP32_SIMT 0 /* exact fp32 FFMA path */
 #define CLB_MM_TF32X3 1    /* tcgen05 kind::tf32, 3-pass split (hi*hi + hi*lo + lo*hi), fp32 accum in TMEM */
 #define CLB_MM_TF32X1 2    /* tcgen05 kind::tf32 single pass (fast, NOT parity mode) */
+#define CLB_MM_BF16X3 3    /* conv fwd/dgrad on tcgen05 kind::f16 with a bf16 hi/lo 3-pass split (half the tensor work of
+                              TF32X3, ~1e-5 per dot product); everything else as CLB_MM_TF32X3 */
 
 const char* clb_last_error(void);
 int clb_version(void);

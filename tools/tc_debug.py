@@ -67,6 +67,13 @@ if __name__ == "__main__":
         run((2, 3, 16, 16, 8), 1)
         print("tc_debug first done")
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "bf16":          # mode 3: bf16 hi/lo split for fwd / dgrad (C % 64 == 0)
+        run((2, 64, 8, 8, 128), 3, structured=True)
+        for shp in [(2, 64, 8, 8, 128), (9, 64, 32, 32, 128), (7, 256, 8, 8, 512), (3, 128, 16, 16, 64), (25, 512, 4, 4, 512)]:
+            run(shp, 3)
+            run(shp, 1)
+        print("tc_debug bf16 done")
+        sys.exit(0)
     run((2, 32, 8, 8, 128), 2, structured=True)
     run((2, 32, 8, 8, 128), 2)
     run((2, 32, 8, 8, 128), 1)

@@ -296,10 +296,22 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __rest
 // in order by the last stage.  No atomics: bit-reproducible.
 // WRITE_LO: the same pass also writes the lo plane (x - trunc19(x)) of dY that the TMA-fed wgrad kernel consumes, so dY
 // is read once for both (the summation order of the bias partials is unchanged).
-template <bool WRITE_LO>
+// WRITE_LO == 2: instead of the fp32 lo plane, the bf16 hi plane (into dy_lo) and bf16 lo plane (into dy_lo2) of dY for
+// the kind::f16 wgrad kernel (hi = bf16_rn(x), lo = bf16_rn(x - hi)).
+__device__ __forceinline__ void bf16_split_pair(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    uint32_t a = __float_as_uint(v0), b = __float_as_uint(v1);
+    a += 0x7FFFu + ((a >> 16) & 1u);
+    b += 0x7FFFu + ((b >> 16) & 1u);
+    hi = (a >> 16) | (b & 0xFFFF0000u);
+    uint32_t c = __float_as_uint(v0 - __uint_as_float(a & 0xFFFF0000u)), d = __float_as_uint(v1 - __uint_as_float(b & 0xFFFF0000u));
+    c += 0x7FFFu + ((c >> 16) & 1u);
+    d += 0x7FFFu + ((d >> 16) & 1u);
+    lo = (c >> 16) | (d & 0xFFFF0000u);
+}
+template <int WRITE_LO>
 __global__ void __launch_bounds__(256) conv_bias_grad_partial_kernel(const float* __restrict__ dy, float* __restrict__ part,
-                                                                     float* __restrict__ dy_lo, int N, int K, int PQ,
-                                                                     int imgs_per_split) {
+                                                                     float* __restrict__ dy_lo, uint16_t* __restrict__ dy_lo2,
+                                                                     int N, int K, int PQ, int imgs_per_split) {
     const int k = blockIdx.x, sp = blockIdx.y;
     const int n0 = sp * imgs_per_split, n1 = min(N, n0 + imgs_per_split);
     float s = 0.f;
@@ -311,7 +323,13 @@ __global__ void __launch_bounds__(256) conv_bias_grad_partial_kernel(const float
             const int64_t row = ((int64_t)img * K + k) * PQ;
             const float4 v = __ldg(reinterpret_cast<const float4*>(dy + row) + q);
             s += (v.x + v.y) + (v.z + v.w);
-            if (WRITE_LO) {
+            if (WRITE_LO == 2) {
+                uint32_t h0, h1, l0, l1;
+                bf16_split_pair(v.x, v.y, h0, l0);
+                bf16_split_pair(v.z, v.w, h1, l1);
+                reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(dy_lo) + row)[q] = make_uint2(h0, h1);
+                reinterpret_cast<uint2*>(dy_lo2 + row)[q] = make_uint2(l0, l1);
+            } else if (WRITE_LO == 1) {
                 float4 o;
                 o.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
                 o.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
@@ -353,14 +371,21 @@ static inline int bias_grad_splits(int N, int K) {
 static void conv_bias_grad(const float* dy, float* db, float* scratch, int N, int K, int PQ, cudaStream_t s) {
     const int want = bias_grad_splits(N, K);
     const int per = (N + want - 1) / want, nsplit = (N + per - 1) / per;
-    conv_bias_grad_partial_kernel<false><<<dim3(K, nsplit), 256, 0, s>>>(dy, scratch, nullptr, N, K, PQ, per); clb::count_launch();
+    conv_bias_grad_partial_kernel<0><<<dim3(K, nsplit), 256, 0, s>>>(dy, scratch, nullptr, nullptr, N, K, PQ, per); clb::count_launch();
     conv_bias_grad_final_kernel<<<(K + 127) / 128, 128, 0, s>>>(scratch, db, K, nsplit); clb::count_launch();
 }
 // First half of conv_bias_grad fused with the lo-plane split of dY (PQ % 4 == 0); conv_bias_grad_finish() is the rest.
 void conv_bias_partials_and_lo(const float* dy, float* dy_lo, float* scratch, int N, int K, int PQ, cudaStream_t s) {
     const int want = bias_grad_splits(N, K);
     const int per = (N + want - 1) / want, nsplit = (N + per - 1) / per;
-    conv_bias_grad_partial_kernel<true><<<dim3(K, nsplit), 256, 0, s>>>(dy, scratch, dy_lo, N, K, PQ, per); clb::count_launch();
+    conv_bias_grad_partial_kernel<1><<<dim3(K, nsplit), 256, 0, s>>>(dy, scratch, dy_lo, nullptr, N, K, PQ, per); clb::count_launch();
+}
+void conv_bias_partials_and_bf16(const float* dy, uint16_t* dy_hi, uint16_t* dy_lo, float* scratch, int N, int K, int PQ,
+                                 cudaStream_t s) {
+    const int want = bias_grad_splits(N, K);
+    const int per = (N + want - 1) / want, nsplit = (N + per - 1) / per;
+    conv_bias_grad_partial_kernel<2><<<dim3(K, nsplit), 256, 0, s>>>(dy, scratch, reinterpret_cast<float*>(dy_hi), dy_lo, N, K, PQ,
+                                                                     per); clb::count_launch();
 }
 static void conv_bias_grad_finish(const float* scratch, float* db, int N, int K, cudaStream_t s) {
     const int want = bias_grad_splits(N, K);

@@ -198,7 +198,196 @@ static int launch_fwd(const ALoad& A, const uint16_t* w_hi, const uint16_t* w_lo
     return CLB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- wgrad
+// dW^T tile [kout 128][tap rows 128] += dY[kout][64 pixels] * X_taps[tap][64 pixels]^T.  A = dY rows by TMA from the bf16
+// hi / lo planes (written by the bias-partials pass, which reads dY anyway), B = filter-tap rows gathered by three loader
+// groups (the +-1 pixel shifts are not TMA-legal in NCHW) and stored as bf16 hi / lo rows; both operands in swizzled
+// smem (SS MMAs), split accumulators, deterministic split-K.  Same pipeline as tc3::wgrad_mixed_kernel with half the
+// operand bytes per K element: that kernel is bound by the shared-memory port (l1tex data pipe 89 %).
+constexpr int kWgGroups = 3, kWgStages = 3;
+constexpr int kWgWarpTma = 4 * kWgGroups, kWgWarpMma = kWgWarpTma + 1;
+constexpr int kWgThreads = (kWgWarpMma + 1) * 32;      // 448
+constexpr int kTile = BM * 128;                        // 128 rows x 64 bf16 = 16 KB
+constexpr int kWgStage = 4 * kTile;                    // A_hi, A_lo, B_hi, B_lo
+constexpr int kWgSmem = kWgStages * kWgStage + 256 + 1024;
+static_assert(kWgGroups == kWgStages, "group g must own stage g");
+
+__device__ __forceinline__ void umma_bf16_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+// thread tg holds, for rows (tg >> 3) + 16 i, pixels 4 (tg & 7) .. +3 of both 32-pixel halves of the K block
+__device__ __forceinline__ void store_taps_bf16(const clb::tcl::BRegs<128>& g0, const clb::tcl::BRegs<128>& g1, int tg,
+                                                uint32_t tile_hi, uint32_t tile_lo) {
+    const int c = tg & 7, r0 = tg >> 3;                 // (r & 7) == (r0 & 7) for every row r0 + 16 i
+    const uint32_t sub = (uint32_t)(c & 1) * 8u;
+    const uint32_t off_a = (uint32_t)r0 * 128u + (uint32_t)((((c >> 1)) ^ (r0 & 7)) << 4) + sub;        // pixels 4c..
+    const uint32_t off_b = (uint32_t)r0 * 128u + (uint32_t)(((4 + (c >> 1)) ^ (r0 & 7)) << 4) + sub;    // pixels 32 + 4c..
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint32_t h0, h1, l0, l1;
+        split_pair(g0.v[i].x, g0.v[i].y, h0, l0);
+        split_pair(g0.v[i].z, g0.v[i].w, h1, l1);
+        st_shared_v2(tile_hi + off_a + (uint32_t)i * 2048u, h0, h1);
+        st_shared_v2(tile_lo + off_a + (uint32_t)i * 2048u, l0, l1);
+        split_pair(g1.v[i].x, g1.v[i].y, h0, l0);
+        split_pair(g1.v[i].z, g1.v[i].w, h1, l1);
+        st_shared_v2(tile_hi + off_b + (uint32_t)i * 2048u, h0, h1);
+        st_shared_v2(tile_lo + off_b + (uint32_t)i * 2048u, l0, l1);
+    }
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_bf16_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_dy_lo,
+                  clb::tcl::TapRows<128> B, clb::tcl::EpiSplitK epi, int kb_per_img, int num_kb_total, int kb_per_split) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar = base + kWgStages * kWgStage;
+    const uint32_t a_full = bar, b_full = bar + 8 * kWgStages, empty = bar + 16 * kWgStages;
+    const uint32_t bar_tmem = empty + 8 * kWgStages, slot = bar_tmem + 8;
+    uint32_t* slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (slot - smem_u32(smem_raw)));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * 128, z = blockIdx.z;
+    const int kb_begin = z * kb_per_split;
+    const int nkb = max(min(num_kb_total, kb_begin + kb_per_split) - kb_begin, 0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kWgStages; ++s) {
+            mbar_init(a_full + 8 * s, 1);
+            mbar_init(b_full + 8 * s, 4);
+            mbar_init(empty + 8 * s, 1);
+        }
+        mbar_init(bar_tmem, 1);
+        fence_barrier_init();
+        tma::prefetch_desc(&map_dy);
+        tma::prefetch_desc(&map_dy_lo);
+    }
+    if (warp == kWgWarpMma) tmem_alloc(slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *slot_ptr;
+
+    if (warp < kWgWarpTma) {
+        const int group = warp >> 2, tg = threadIdx.x & 127;
+        const typename clb::tcl::TapRows<128>::Ctx bctx = B.prep(tg, n0);
+        for (int i = group; i < nkb; i += kWgGroups) {
+            clb::tcl::BRegs<128> g0, g1;
+            B.load(2 * (kb_begin + i), tg, bctx, g0);              // TapRows counts 32-pixel blocks
+            B.load(2 * (kb_begin + i) + 1, tg, bctx, g1);
+            const int s = i % kWgStages;
+            mbar_wait(empty + 8 * s, (((uint32_t)(i / kWgStages)) & 1u) ^ 1u);
+            const uint32_t st = base + (uint32_t)s * kWgStage;
+            store_taps_bf16(g0, g1, tg, st + 2 * kTile, st + 3 * kTile);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_full + 8 * s);
+        }
+    } else if (warp == kWgWarpTma) {
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % kWgStages;
+                mbar_wait(empty + 8 * s, (((uint32_t)(i / kWgStages)) & 1u) ^ 1u);
+                const int kb = kb_begin + i;
+                const int img = kb / kb_per_img, pq0 = (kb - img * kb_per_img) * BK2;
+                tma::mbar_arrive_expect_tx(a_full + 8 * s, (uint32_t)(2 * kTile));
+                const uint32_t st = base + (uint32_t)s * kWgStage;
+                tma::load_3d(st, &map_dy, a_full + 8 * s, pq0, m0, img);
+                tma::load_3d(st + kTile, &map_dy_lo, a_full + 8 * s, pq0, m0, img);
+            }
+        }
+    } else if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(128);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % kWgStages;
+            const uint32_t ph = ((uint32_t)(i / kWgStages)) & 1u;
+            mbar_wait(a_full + 8 * s, ph);
+            mbar_wait(b_full + 8 * s, ph);
+            tc_fence_after();
+            const uint32_t st = base + (uint32_t)s * kWgStage;
+            const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + kTile);
+            const uint64_t b_hi = make_desc(st + 2 * kTile), b_lo = make_desc(st + 3 * kTile);
+#pragma unroll
+            for (int k = 0; k < BK2 / 16; ++k) {
+                umma_bf16_ss(tmem + 128, a_lo + 2 * k, b_hi + 2 * k, idesc, (i | k) != 0);
+                umma_bf16_ss(tmem + 128, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+                umma_bf16_ss(tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (i | k) != 0);
+            }
+            umma_commit(empty + 8 * s);
+        }
+        umma_commit(bar_tmem);
+    }
+
+    if (warp < 8) {
+        if (nkb > 0) {
+            mbar_wait(bar_tmem, 0);
+            tc_fence_after();
+        }
+        const int lane_grp = warp & 3, col_half = warp >> 2;
+        const int m = m0 + lane_grp * 32 + lane;
+#pragma unroll 1
+        for (int c = 0; c < 64; c += 16) {
+            const int col = col_half * 64 + c;
+            uint32_t r[16];
+            if (nkb > 0) {
+                uint32_t r2[16];
+                tmem_ld16(tmem + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)col, r);
+                tmem_ld16(tmem + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(128 + col), r2);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[j] = 0u;
+            }
+            epi.store16(m, n0 + col, r, z);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kWgWarpMma) tmem_dealloc(tmem, 256);
+}
+
 }  // namespace tc4
+
+// wgrad through the bf16 kernel: whole 64-pixel K blocks inside one image, 16-byte pixel chunks
+bool tc4_wgrad_supported(int H, int W) { return (H * W) % 64 == 0 && (W % 4) == 0; }
+
+// dy_planes: bf16 hi plane [N][K][PQ] followed by the lo plane (written by conv_bias_partials_and_bf16 -- the same
+// workspace region the fp32 lo plane of the TF32 kernel uses).  splits32 / kb_per_split32: the 32-pixel-block plan the
+// workspace was sized for; returns the number of split-K slices actually written in *splits_out.
+int tc4_conv_wgrad(const float* x, const float* dy, float* ws_partials, float* bias_part, float* dy_planes, int N, int C, int H,
+                   int W, int K, int R, int S, int pad, int splits32, int kb_per_split32, int* splits_out, cudaStream_t s) {
+    using namespace tc4;
+    const int PQ = H * W, n_rows = R * S * C, npix = N * PQ;
+    uint16_t* hi = reinterpret_cast<uint16_t*>(dy_planes);
+    uint16_t* lo = hi + (size_t)N * K * PQ;
+    clb::conv_bias_partials_and_bf16(dy, hi, lo, bias_part, N, K, PQ, s);
+    CUtensorMap m_hi, m_lo;
+    const uint64_t dims[3] = {(uint64_t)PQ, (uint64_t)K, (uint64_t)N};
+    const uint64_t str[2] = {(uint64_t)PQ * 2, (uint64_t)K * PQ * 2};
+    const uint32_t box[3] = {(uint32_t)BK2, 128, 1};
+    int rc = tma::encode_bf16(&m_hi, hi, 3, dims, str, box, true);
+    if (rc) return rc;
+    rc = tma::encode_bf16(&m_lo, lo, 3, dims, str, box, true);
+    if (rc) return rc;
+    const int nkb = npix / BK2, per = (kb_per_split32 + 1) / 2, splits = (nkb + per - 1) / per;
+    if (splits > splits32) { set_error("tc4_conv_wgrad: split plan mismatch (%d > %d)", splits, splits32); return CLB_EINVAL; }
+    *splits_out = splits;
+    clb::tcl::TapRows<128> B{x, C, H, W, R, S, pad, H, W, n_rows, npix, FastDiv32(PQ), FastDiv32(W), FastDiv32(C), FastDiv32(S)};
+    clb::tcl::EpiSplitK e{ws_partials, K, n_rows, (int64_t)K * n_rows};
+    dim3 grid((K + BM - 1) / BM, (n_rows + 127) / 128, splits);
+    static bool configured = false;
+    if (!configured) { CLB_CUDA(cudaFuncSetAttribute(wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem)); configured = true; }
+    wgrad_bf16_kernel<<<grid, kWgThreads, kWgSmem, s>>>(m_hi, m_lo, B, e, PQ / BK2, nkb, per); clb::count_launch();
+    return CLB_OK;
+}
 
 // C = reduction channels of the conv seen as forward (C_in for fwd, K_out for dgrad): whole 64-element K blocks per tap
 bool tc4_fwd_supported(int C) { return (C % 64) == 0; }

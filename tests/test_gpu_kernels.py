@@ -9,6 +9,8 @@ Tolerances (normalised max error, tests/util.rel_err):
 import ctypes
 
 import numpy as np
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -18,7 +20,7 @@ from oracle import restate
 from tests.util import rel_err
 
 pytestmark = pytest.mark.gpu
-DEFAULT_MODE = 1      # the library default (CLB_MM_TF32X3); tests that switch modes restore it
+DEFAULT_MODE = int(os.environ.get("CLB_MM_MODE", "1"))      # the library default; tests that switch modes restore it
 
 
 @pytest.fixture(scope="module")
@@ -98,7 +100,7 @@ CONVS = [  # N, C, H, W, K, R, stride, pad
 
 
 @pytest.mark.parametrize("shape", CONVS)
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 3])
 def test_conv2d_fwd_bwd(capi, shape, mode):
     N, C, H, W, K, R, stride, pad = shape
     capi.call("clb_set_matmul_mode", mode)
@@ -136,7 +138,7 @@ def test_conv2d_fwd_bwd(capi, shape, mode):
 
 
 @pytest.mark.parametrize("M,inf,outf", [(16, 64, 32), (200, 2048, 512), (37, 512, 20), (5, 9216, 4096), (200, 4096, 20)])
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 3])
 def test_linear_fwd_bwd(capi, M, inf, outf, mode):
     capi.call("clb_set_matmul_mode", mode)
     tol = 2e-5 if mode == 0 else 1e-4

@@ -15,6 +15,8 @@ What can be asserted tightly on a deep ReLU / max-pool net, and what cannot:
     no ReLU / pool decision lies within 1.8e-4 of its boundary, i.e. no flips can occur."""
 import copy
 
+import os
+
 import pytest
 import torch
 
@@ -22,7 +24,7 @@ from oracle import restate
 from tests.util import rel_err
 
 pytestmark = pytest.mark.gpu
-DEFAULT_MODE = 1      # the library default (CLB_MM_TF32X3); tests that switch modes restore it
+DEFAULT_MODE = int(os.environ.get("CLB_MM_MODE", "1"))      # the library default; tests that switch modes restore it
 TOL = 1e-4
 GRAD_TOL = 1e-1      # discontinuity-limited sanity bound, see module docstring
 
@@ -34,7 +36,7 @@ def _models():
 
 
 @pytest.mark.parametrize("name", ["VGG11", "small_VGG9", "alexnet"])
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 3])
 def test_model_step_fisher_mas(name, mode):
     from clsurvey_b200 import _capi
     from clsurvey_b200.engine import LOSS_SUM_SQ, Engine
@@ -96,9 +98,16 @@ def test_model_step_fisher_mas(name, mode):
             losses.append(eng.read_loss_correct()[0])
         assert abs(losses[0] - losses_ref[0]) <= TOL * abs(losses_ref[0]), (losses, losses_ref)     # forward: tight
         assert abs(losses[1] - losses_ref[1]) <= 1e-2 * abs(losses_ref[1]), (losses, losses_ref)    # after one update
-        for (n, p), pr in zip(named, ref.parameters()):
+        # one flipped ReLU moves a layer's weight gradient by ~1/sqrt(#output positions): the 4x4 layers of VGG-11 see
+        # only 8 * 16 = 128 positions at this batch size, so their bound is 2/sqrt(128) = 0.18 (seen: 0.14 in one mode)
+        positions = {}
+        for op in eng.ops:
+            if op["kind"] == "conv":
+                positions[op["w"]] = B * op["out_shape"][1] * op["out_shape"][2]
+        for i, ((n, p), pr) in enumerate(zip(named, ref.parameters())):
             if p.dim() > 1:      # biases start at 0: after two steps they ARE the (discontinuity-limited) gradient
-                assert rel_err(p.data, pr.data) <= GRAD_TOL, ("theta", n)
+                tol_i = max(GRAD_TOL, 2.0 / positions[i] ** 0.5) if i in positions else GRAD_TOL
+                assert rel_err(p.data, pr.data) <= tol_i, ("theta", n)
     finally:
         _capi.call("clb_set_matmul_mode", DEFAULT_MODE)
 
@@ -146,7 +155,7 @@ def test_full_batch_properties_vgg11():
     assert rel_err(om, 2 * one) <= 1e-6
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_tc_chain_decision_margins(mode):
     """A tcgen05-eligible chain (3->32 | pool | 32->32 -> 32->64 | pool, 8x8 inputs, batch 2: M = 32 pixel rows < one MMA
     tile, W = 4) with seed 37, for which every ReLU pre-activation and every max-pool runner-up is >= 1.8e-4 (relative)

@@ -317,7 +317,7 @@ def run_gpu_arm(args):
     if rank == 0:
         conv_tf = conv_f * per / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         mode_name = {0: "fp32 FFMA (SIMT)", 1: "tf32x3 tcgen05", 2: "tf32x1 tcgen05",
-                     3: "bf16x3 tcgen05 (conv fwd/dgrad) + tf32x3"}[args.mm_mode]
+                     3: "bf16x3 tcgen05 (conv fwd/dgrad/wgrad) + tf32x3 (rest)"}[args.mm_mode]
         line = {
             "metric": "images/sec/task", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -337,6 +337,10 @@ def run_gpu_arm(args):
                          "frac": conv_tf / pk["tensor"], "traffic": None,
                          "kernel": "conv2d implicit-GEMM fwd+wgrad+dgrad (%d launches/step, %s)" % (n_conv_launch, mode_name),
                          "algorithmic_gflop_per_step": conv_f * per / 1e9, "ms_per_step_in_kernel": conv_ms,
+                         # the fp32-parity split issues 3 MMAs per algorithmic one (bf16 rate in mode 3, tf32 = half of
+                         # it in mode 1): fraction of the rate the tensor pipe can give to THIS arithmetic
+                         "mma_passes": {0: 0, 1: 3, 2: 1, 3: 3}[args.mm_mode],
+                         "frac_of_split_ceiling": (conv_tf * {0: 0, 1: 6, 2: 2, 3: 3}[args.mm_mode] / pk["tensor"]),
                          "share_of_step": conv_ms / (ms_eager / args.steps),
                          "measured": "CUDA events around every conv launch over %d eager steps (%.3f ms/step eager, "
                                      "%.3f ms/step as replayed graph)" % (args.steps, ms_eager / args.steps, ms / args.steps),
@@ -367,8 +371,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="clb", choices=["clb", "reference"])
     ap.add_argument("--model", default="VGG11_cl_512_512")
-    ap.add_argument("--mm-mode", type=int, default=int(os.environ.get("CLB_MM_MODE", "1")),
-                    help="0 exact-fp32 FFMA, 1 tcgen05 TF32x3 (fp32-parity mode, default), 2 tcgen05 TF32x1 (fast, non-parity)")
+    ap.add_argument("--mm-mode", type=int, default=int(os.environ.get("CLB_MM_MODE", "3")),
+                    help="0 exact-fp32 FFMA, 1 tcgen05 TF32x3 (fp32 parity), 2 tcgen05 TF32x1 (fast, non-parity), "
+                         "3 tcgen05 bf16x3 conv kernels + TF32x3 elsewhere (fp32 parity, default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--global-batch", type=int, default=200, help="diagnostics only: the BASELINE workload is 200")
     ap.add_argument("--no-graph", action="store_true")

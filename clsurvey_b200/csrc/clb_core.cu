@@ -6,7 +6,8 @@
 
 namespace clb {
 static thread_local char g_err[512] = "";
-// default: tensor-core parity mode (3-pass TF32 split); CLB_MM_MODE=0/1/2/3 overrides at first use
+// default: tensor-core parity mode (bf16 hi/lo split for the conv kernels, 3-pass TF32 split elsewhere); CLB_MM_MODE=0/1/2/3
+// overrides at first use
 static int g_mm_mode = -1;
 
 void set_error(const char* fmt, ...) {
@@ -31,7 +32,7 @@ int sm_count() {
 int mm_mode() {
     if (g_mm_mode < 0) {
         const char* e = getenv("CLB_MM_MODE");
-        g_mm_mode = (e && e[0] >= '0' && e[0] <= '3' && e[1] == 0) ? (e[0] - '0') : CLB_MM_TF32X3;
+        g_mm_mode = (e && e[0] >= '0' && e[0] <= '3' && e[1] == 0) ? (e[0] - '0') : CLB_MM_BF16X3;
     }
     return g_mm_mode;
 }

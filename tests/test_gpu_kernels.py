@@ -20,7 +20,7 @@ from oracle import restate
 from tests.util import rel_err
 
 pytestmark = pytest.mark.gpu
-DEFAULT_MODE = int(os.environ.get("CLB_MM_MODE", "1"))      # the library default; tests that switch modes restore it
+DEFAULT_MODE = int(os.environ.get("CLB_MM_MODE", "3"))      # the library default; tests that switch modes restore it
 
 
 @pytest.fixture(scope="module")

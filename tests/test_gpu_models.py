@@ -24,7 +24,7 @@ from oracle import restate
 from tests.util import rel_err
 
 pytestmark = pytest.mark.gpu
-DEFAULT_MODE = int(os.environ.get("CLB_MM_MODE", "1"))      # the library default; tests that switch modes restore it
+DEFAULT_MODE = int(os.environ.get("CLB_MM_MODE", "3"))      # the library default; tests that switch modes restore it
 TOL = 1e-4
 GRAD_TOL = 1e-1      # discontinuity-limited sanity bound, see module docstring
 

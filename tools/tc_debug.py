@@ -54,7 +54,7 @@ def run(shape, mode, structured=False):
     _capi.call("clb_conv2d_dgrad", dyd.data_ptr(), wd.data_ptr(), dx.data_ptr(), wws.data_ptr(), N, C, H, W, K, 3, 3, 1, 1, S())
     torch.cuda.synchronize()
     print("   dgrad rel err %.3e" % rel(dx, xr.grad), flush=True)
-    _capi.call("clb_set_matmul_mode", 1)
+    _capi.call("clb_set_matmul_mode", 3)
 
 
 if __name__ == "__main__":

@@ -69,7 +69,7 @@ int tc_conv_wgrad(const float* x, const float* dy, float* dw, float* ws, float* 
 void conv_bias_partials_and_lo(const float* dy, float* dy_lo, float* scratch, int N, int K, int PQ, cudaStream_t s);
 void conv_bias_partials_and_bf16(const float* dy, uint16_t* dy_hi, uint16_t* dy_lo, float* scratch, int N, int K, int PQ,
                                  cudaStream_t s);
-bool tc4_wgrad_supported(int H, int W);
+bool tc4_wgrad_supported(int H, int W, int R, int S);
 int tc4_conv_wgrad(const float* x, const float* dy, float* ws_partials, float* bias_part, float* dy_planes, int N, int C, int H,
                    int W, int K, int R, int S, int pad, int splits32, int kb_per_split32, int* splits_out, cudaStream_t s);
 bool tc3_linear_supported(int M, int in, int out);

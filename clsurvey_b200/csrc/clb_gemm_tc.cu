@@ -479,7 +479,7 @@ int tc_conv_wgrad(const float* x, const float* dy, float* dw, float* ws, float* 
         tc3_wgrad_plan(N, C, H, W, K, R, S, &splits, &per);
         size_t off = ((size_t)splits * K * n_rows + 7) & ~(size_t)3;              // keep the lo plane 16-byte aligned
         float* dy_lo = ws + off;
-        if (mm_mode() == CLB_MM_BF16X3 && with_lo && bias_part && tc4_wgrad_supported(H, W)) {
+        if (mm_mode() == CLB_MM_BF16X3 && with_lo && bias_part && tc4_wgrad_supported(H, W, R, S)) {
             int used = splits;
             int rc4 = tc4_conv_wgrad(x, dy, ws, bias_part, dy_lo, N, C, H, W, K, R, S, pad, splits, per, &used, s);
             if (rc4) return rc4;

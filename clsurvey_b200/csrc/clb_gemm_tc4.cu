@@ -103,14 +103,24 @@ fwd_bf16_kernel(ALoad A, const __grid_constant__ CUtensorMap map_w, const __grid
         const typename ALoad::Ctx actx = A.prep(m0 + tg);
         for (int i = group; i < nkb; i += kGroups) {
             float v0[BK], v1[BK];                                  // the two 32-element halves of this 64-element K block
+#ifdef CLB_DIAG_NO_A_LOAD                                          // timing experiments only (results are garbage)
+#pragma unroll
+            for (int j = 0; j < BK; ++j) { v0[j] = (float)(i + j + tg); v1[j] = (float)(i - j + tg); }
+#else
             A.row(2 * i, actx, v0);
             A.row(2 * i + 1, actx, v1);
+#endif
             uint32_t hi[32], lo[32];
+#ifdef CLB_DIAG_NO_SPLIT
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { hi[j] = __float_as_uint(v0[j]); lo[j] = __float_as_uint(v1[j]); }
+#else
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 split_pair(v0[2 * j], v0[2 * j + 1], hi[j], lo[j]);
                 split_pair(v1[2 * j], v1[2 * j + 1], hi[16 + j], lo[16 + j]);
             }
+#endif
             const int s = i % kStagesA;
             mbar_wait(a_empty + 8 * s, (((uint32_t)(i / kStagesA)) & 1u) ^ 1u);
             tc_fence_after();
@@ -143,12 +153,14 @@ fwd_bf16_kernel(ALoad A, const __grid_constant__ CUtensorMap map_w, const __grid
             const uint32_t st = base + (uint32_t)sb * L::kStageB;
             const uint64_t b_hi = make_desc(st), b_lo = make_desc(st + L::kBTile);
             const uint32_t a_hi = tmem_a0 + (uint32_t)sa * L::kAStageCols, a_lo = a_hi + 32;
+#ifndef CLB_DIAG_NO_MMA
 #pragma unroll
             for (int k = 0; k < BK2 / 16; ++k) {
                 umma_bf16_ts(tmem + BN, a_lo + 8 * k, b_hi + 2 * k, idesc, (i | k) != 0);
                 umma_bf16_ts(tmem + BN, a_hi + 8 * k, b_lo + 2 * k, idesc, 1);
                 umma_bf16_ts(tmem, a_hi + 8 * k, b_hi + 2 * k, idesc, (i | k) != 0);
             }
+#endif
             umma_commit(a_empty + 8 * sa);
             umma_commit(b_empty + 8 * sb);
         }
@@ -220,33 +232,72 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t d, uint64_t a, uint64_t b,
         ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc)
         : "memory");
 }
-__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
-    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
-}
-// thread tg holds, for rows (tg >> 3) + 16 i, pixels 4 (tg & 7) .. +3 of both 32-pixel halves of the K block
-__device__ __forceinline__ void store_taps_bf16(const clb::tcl::BRegs<128>& g0, const clb::tcl::BRegs<128>& g1, int tg,
-                                                uint32_t tile_hi, uint32_t tile_lo) {
-    const int c = tg & 7, r0 = tg >> 3;                 // (r & 7) == (r0 & 7) for every row r0 + 16 i
-    const uint32_t sub = (uint32_t)(c & 1) * 8u;
-    const uint32_t off_a = (uint32_t)r0 * 128u + (uint32_t)((((c >> 1)) ^ (r0 & 7)) << 4) + sub;        // pixels 4c..
-    const uint32_t off_b = (uint32_t)r0 * 128u + (uint32_t)(((4 + (c >> 1)) ^ (r0 & 7)) << 4) + sub;    // pixels 32 + 4c..
+// Filter-tap rows for 64-pixel K blocks: thread tg owns the 8-pixel chunk (tg & 7) of rows (tg >> 3) + 16 i, i < 8.
+// W % 8 == 0, so a chunk never leaves its image row and starts 32-byte aligned: the window shifted by ds in {-1, 0, +1}
+// is two aligned 16-byte loads plus ONE neighbour element (zero at the image border), instead of eight 4-byte loads that
+// each touch every line of the warp's four rows (the LSU wavefront count was what bound the first version: l1tex data
+// pipe 88 %).  One 16-byte swizzled store per plane and row.
+struct TapChunks {
+    const float* x; int C, H, W, R, S, pad, n_rows, k_total;
+    FastDiv32 dPQ, dW, dC, dS;
+    struct Ctx { int off[8]; signed char dr[8], ds[8]; };            // off = c*H*W + dr*W (aligned part), INT_MIN = masked row
+    struct Regs { float4 a[8], b[8]; float nb[8]; };
+    __device__ __forceinline__ Ctx prep(int tg, int row0) const {
+        Ctx t;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        uint32_t h0, h1, l0, l1;
-        split_pair(g0.v[i].x, g0.v[i].y, h0, l0);
-        split_pair(g0.v[i].z, g0.v[i].w, h1, l1);
-        st_shared_v2(tile_hi + off_a + (uint32_t)i * 2048u, h0, h1);
-        st_shared_v2(tile_lo + off_a + (uint32_t)i * 2048u, l0, l1);
-        split_pair(g1.v[i].x, g1.v[i].y, h0, l0);
-        split_pair(g1.v[i].z, g1.v[i].w, h1, l1);
-        st_shared_v2(tile_hi + off_b + (uint32_t)i * 2048u, h0, h1);
-        st_shared_v2(tile_lo + off_b + (uint32_t)i * 2048u, l0, l1);
+        for (int i = 0; i < 8; ++i) {
+            const int n = row0 + (tg >> 3) + 16 * i;
+            const uint32_t rs = dC.div(n), c = n - rs * C;
+            const uint32_t r = dS.div(rs), s = rs - r * S;
+            t.dr[i] = (signed char)((int)r - pad);
+            t.ds[i] = (signed char)((int)s - pad);
+            t.off[i] = n < n_rows ? (int)c * H * W + t.dr[i] * W : INT_MIN;
+        }
+        return t;
     }
-}
+    __device__ __forceinline__ void load(int kb, int tg, const Ctx& t, Regs& g) const {
+        const int pix = kb * BK2 + (tg & 7) * 8;
+        const uint32_t img = dPQ.div(pix), pq = pix - img * (H * W);
+        const uint32_t p = dW.div(pq), q0 = pq - p * W;
+        const bool kok = pix < k_total;
+        const float* base = x + (size_t)img * C * H * W + (int)p * W + (int)q0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const bool rok = kok && t.off[i] != INT_MIN && (unsigned)((int)p + t.dr[i]) < (unsigned)H;
+            const float* src = base + (rok ? t.off[i] : 0);
+            g.a[i] = rok ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0, 0, 0, 0);
+            g.b[i] = rok ? __ldg(reinterpret_cast<const float4*>(src) + 1) : make_float4(0, 0, 0, 0);
+            const int ds = t.ds[i];
+            const bool nok = rok && (ds < 0 ? q0 > 0 : (ds > 0 && (int)q0 + 8 < W));
+            g.nb[i] = nok ? __ldg(src + (ds < 0 ? -1 : 8)) : 0.f;
+        }
+    }
+    // shift, split into bf16 hi / lo and store: row r = (tg >> 3) + 16 i, 16-byte chunk (tg & 7) ^ (r & 7)
+    __device__ __forceinline__ void store(const Ctx& t, const Regs& g, int tg, uint32_t tile_hi, uint32_t tile_lo) const {
+        const int c = tg & 7, r0 = tg >> 3;
+        const uint32_t off0 = (uint32_t)r0 * 128u + (uint32_t)((c ^ (r0 & 7)) << 4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float v[8] = {g.a[i].x, g.a[i].y, g.a[i].z, g.a[i].w, g.b[i].x, g.b[i].y, g.b[i].z, g.b[i].w};
+            const int ds = t.ds[i];
+            float u[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float left = j > 0 ? v[j - 1] : g.nb[i], right = j < 7 ? v[j + 1] : g.nb[i];
+                u[j] = ds < 0 ? left : (ds > 0 ? right : v[j]);
+            }
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) split_pair(u[2 * j], u[2 * j + 1], h[j], l[j]);
+            st_shared_v4(tile_hi + off0 + (uint32_t)i * 2048u, h[0], h[1], h[2], h[3]);
+            st_shared_v4(tile_lo + off0 + (uint32_t)i * 2048u, l[0], l[1], l[2], l[3]);
+        }
+    }
+};
 
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_bf16_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_dy_lo,
-                  clb::tcl::TapRows<128> B, clb::tcl::EpiSplitK epi, int kb_per_img, int num_kb_total, int kb_per_split) {
+                  TapChunks B, clb::tcl::EpiSplitK epi, int kb_per_img, int num_kb_total, int kb_per_split) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar = base + kWgStages * kWgStage;
@@ -277,15 +328,14 @@ wgrad_bf16_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
 
     if (warp < kWgWarpTma) {
         const int group = warp >> 2, tg = threadIdx.x & 127;
-        const typename clb::tcl::TapRows<128>::Ctx bctx = B.prep(tg, n0);
+        const TapChunks::Ctx bctx = B.prep(tg, n0);
         for (int i = group; i < nkb; i += kWgGroups) {
-            clb::tcl::BRegs<128> g0, g1;
-            B.load(2 * (kb_begin + i), tg, bctx, g0);              // TapRows counts 32-pixel blocks
-            B.load(2 * (kb_begin + i) + 1, tg, bctx, g1);
+            TapChunks::Regs g;
+            B.load(kb_begin + i, tg, bctx, g);
             const int s = i % kWgStages;
             mbar_wait(empty + 8 * s, (((uint32_t)(i / kWgStages)) & 1u) ^ 1u);
             const uint32_t st = base + (uint32_t)s * kWgStage;
-            store_taps_bf16(g0, g1, tg, st + 2 * kTile, st + 3 * kTile);
+            B.store(bctx, g, tg, st + 2 * kTile, st + 3 * kTile);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(b_full + 8 * s);
@@ -356,8 +406,9 @@ wgrad_bf16_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
 
 }  // namespace tc4
 
-// wgrad through the bf16 kernel: whole 64-pixel K blocks inside one image, 16-byte pixel chunks
-bool tc4_wgrad_supported(int H, int W) { return (H * W) % 64 == 0 && (W % 4) == 0; }
+// wgrad through the bf16 kernel: whole 64-pixel K blocks inside one image
+// and 3x3 filters (the tap loader shifts by at most one pixel), 8-pixel chunks inside an image row
+bool tc4_wgrad_supported(int H, int W, int R, int S) { return (H * W) % 64 == 0 && (W % 8) == 0 && R == 3 && S == 3; }
 
 // dy_planes: bf16 hi plane [N][K][PQ] followed by the lo plane (written by conv_bias_partials_and_bf16 -- the same
 // workspace region the fp32 lo plane of the TF32 kernel uses).  splits32 / kb_per_split32: the 32-pixel-block plan the
@@ -380,7 +431,7 @@ int tc4_conv_wgrad(const float* x, const float* dy, float* ws_partials, float* b
     const int nkb = npix / BK2, per = (kb_per_split32 + 1) / 2, splits = (nkb + per - 1) / per;
     if (splits > splits32) { set_error("tc4_conv_wgrad: split plan mismatch (%d > %d)", splits, splits32); return CLB_EINVAL; }
     *splits_out = splits;
-    clb::tcl::TapRows<128> B{x, C, H, W, R, S, pad, H, W, n_rows, npix, FastDiv32(PQ), FastDiv32(W), FastDiv32(C), FastDiv32(S)};
+    TapChunks B{x, C, H, W, R, S, pad, n_rows, npix, FastDiv32(PQ), FastDiv32(W), FastDiv32(C), FastDiv32(S)};
     clb::tcl::EpiSplitK e{ws_partials, K, n_rows, (int64_t)K * n_rows};
     dim3 grid((K + BM - 1) / BM, (n_rows + 127) / 128, splits);
     static bool configured = false;

@@ -28,10 +28,16 @@ using clb::tcl::PixelRows;
 using clb::tcl::tmem_st32;
 using clb::tcl::tmem_wait_st;
 
-constexpr int kGroups = 4;
+#ifndef CLB_BF16_GROUPS
+#define CLB_BF16_GROUPS 4
+#endif
+#ifndef CLB_BF16_PREFETCH
+#define CLB_BF16_PREFETCH 0                            // 1: issue the next K block's loads before storing the current one
+#endif
+constexpr int kGroups = CLB_BF16_GROUPS;
 constexpr int kWarpTma = 4 * kGroups, kWarpMma = kWarpTma + 1;
 constexpr int kThreads = (kWarpMma + 1) * 32;          // 576
-constexpr int kStagesA = 4, kStagesB = 4;
+constexpr int kStagesA = kGroups, kStagesB = 4;
 constexpr int BK2 = 64;                                // K elements per K block (one 128-byte row of bf16)
 static_assert(kGroups == kStagesA, "group g must own TMEM stage g (parity waits stay within one phase)");
 
@@ -101,7 +107,12 @@ fwd_bf16_kernel(ALoad A, const __grid_constant__ CUtensorMap map_w, const __grid
         const int group = warp >> 2, tg = threadIdx.x & 127;
         const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
         const typename ALoad::Ctx actx = A.prep(m0 + tg);
+#if CLB_BF16_PREFETCH
+        float v0[BK], v1[BK];
+        if (group < nkb) { A.row(2 * group, actx, v0); A.row(2 * group + 1, actx, v1); }
+#endif
         for (int i = group; i < nkb; i += kGroups) {
+#if !CLB_BF16_PREFETCH
             float v0[BK], v1[BK];                                  // the two 32-element halves of this 64-element K block
 #ifdef CLB_DIAG_NO_A_LOAD                                          // timing experiments only (results are garbage)
 #pragma unroll
@@ -109,6 +120,7 @@ fwd_bf16_kernel(ALoad A, const __grid_constant__ CUtensorMap map_w, const __grid
 #else
             A.row(2 * i, actx, v0);
             A.row(2 * i + 1, actx, v1);
+#endif
 #endif
             uint32_t hi[32], lo[32];
 #ifdef CLB_DIAG_NO_SPLIT
@@ -119,6 +131,12 @@ fwd_bf16_kernel(ALoad A, const __grid_constant__ CUtensorMap map_w, const __grid
             for (int j = 0; j < 16; ++j) {
                 split_pair(v0[2 * j], v0[2 * j + 1], hi[j], lo[j]);
                 split_pair(v1[2 * j], v1[2 * j + 1], hi[16 + j], lo[16 + j]);
+            }
+#endif
+#if CLB_BF16_PREFETCH
+            if (i + kGroups < nkb) {                               // in flight across the wait + TMEM store below
+                A.row(2 * (i + kGroups), actx, v0);
+                A.row(2 * (i + kGroups) + 1, actx, v1);
             }
 #endif
             const int s = i % kStagesA;

@@ -270,7 +270,6 @@ def run_gpu_arm(args):
     if sampler:
         sampler.start()
     ms = timed(step_dev, args.steps)
-    clocks = sampler.stop() if sampler else None
     # per-kernel timing of the dominant (conv implicit-GEMM) launches: the same K steps run eagerly with CUDA events
     # around every conv launch (events cannot be read back from inside a replayed graph)
     l0 = _capi.lib().clb_launch_count()
@@ -285,6 +284,8 @@ def run_gpu_arm(args):
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
     e2e = GLOBAL_BATCH * args.steps / (ms_e2e / 1e3)
+    # the sampler ran across the three back-to-back timed regions (value, per-kernel eager pass, e2e): all under load
+    clocks = sampler.stop() if sampler else None
 
     # Fisher / Omega accumulator bandwidth (AlexNet-sized flat buffer, config C2: P = 57,085,780 > L2)
     fisher = None

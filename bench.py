@@ -345,7 +345,10 @@ def run_gpu_arm(args):
                          "share_of_step": conv_ms / (ms_eager / args.steps),
                          "measured": "CUDA events around every conv launch over %d eager steps (%.3f ms/step eager, "
                                      "%.3f ms/step as replayed graph)" % (args.steps, ms_eager / args.steps, ms / args.steps),
-                         "peak_source": pk["src"] + ", bf16 dense sustained"},
+                         "peak_source": pk["src"] + ", bf16 dense sustained",
+                         "traffic_note": "aggregate of all conv launches, so no single per-launch figure; ncu --set full "
+                                         "per launch: 16-106 MB DRAM read + 0-59 MB written = the operand / output bytes "
+                                         "(operands are L2-resident, no re-reads): profiles/r1_ncu_full_bf16*.csv"},
             "roofline_fisher": fisher,
             "cpu_baseline": cpu,
         }

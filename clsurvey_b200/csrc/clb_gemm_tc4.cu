@@ -3,9 +3,11 @@
 // Why: profiles/README.md "Where the conv time goes" -- in the TF32x3 parity mode the forward/dgrad kernel is bound by
 // the tensor pipe itself (3 x the algorithmic flops at the TF32 rate).  kind::f16 with bf16 operands runs K = 16 per MMA
 // at twice the TF32 rate and moves half the operand bytes.  x = hi + lo with hi = bf16_rn(x), lo = bf16_rn(x - hi)
-// leaves a residual <= 2^-18 |x|; the three products hi*hi + hi*lo + lo*hi (fp32 accumulation in TMEM, cross terms in
-// their own accumulator like the TF32 kernels) give ~1e-5 relative error per dot product -- inside the 1e-4 budget of
-// north_star, but ~8x coarser per operand than the TF32 split, hence a separate, opt-in mode.
+// leaves a residual <= 2^-16 |x| (two round-to-nearest steps of 8 bits; the TF32 split leaves 2^-20); the three products
+// hi*hi + hi*lo + lo*hi (fp32 accumulation in TMEM, cross terms in their own accumulator like the TF32 kernels) give
+// ~1e-5 of the natural scale per dot product (tests/test_cpu_split_model.py) -- inside the 1e-4 budget of north_star.
+// On the GPU the per-layer error equals that of the TF32 kernels (3e-6 .. 7e-6 of max|y|, profiles/r1_tc_debug_bf16.log):
+// those are dominated by the truncating TMEM accumulation, of which this kernel does half as much.  Default mode.
 // Operand conventions pinned on the GPU by tools/bf16_probe.py (profiles/r1_bf16_probe.log):
 //   * smem operand: K-major rows of 64 bf16 = one 128-byte swizzled row (same descriptor as the tf32 tiles; one MMA
 //     advances the descriptor by 32 bytes = 16 bf16);

@@ -280,12 +280,13 @@ def run_gpu_arm(args):
     n_conv_launch = len(eng.conv_events) // max(args.steps, 1)
     eng.conv_events = None
     value = GLOBAL_BATCH * args.steps / (ms / 1e3)
+    # the sampler ran across the two back-to-back device-timed regions (graph replay, per-kernel eager pass): all under
+    # load; it is stopped before the end-to-end region so that its nvidia-smi subprocesses never compete with host code
+    clocks = sampler.stop() if sampler else None
     for i in range(min(args.warmup, 3)):
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
     e2e = GLOBAL_BATCH * args.steps / (ms_e2e / 1e3)
-    # the sampler ran across the three back-to-back timed regions (value, per-kernel eager pass, e2e): all under load
-    clocks = sampler.stop() if sampler else None
 
     # Fisher / Omega accumulator bandwidth (AlexNet-sized flat buffer, config C2: P = 57,085,780 > L2)
     fisher = None

@@ -76,6 +76,32 @@ __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uin
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// PixelRows with the plane size H*W as a compile-time constant: the 64 loads of a K block then address
+// [one 64-bit base + immediate offset] instead of carrying ~3 address instructions each (static SASS count of the loader
+// loop: ~500 -> ~300 instructions per thread and K block; the loop is issue-bound, profiles/README.md).
+// Opt-in (CLB_BF16_HWSPEC=1) until it has been measured on the GPU.
+template <int HWC>
+struct PixelRowsHW {
+    const float* x; int C, H, W, R, S, pad, P, Q, M;
+    FastDiv32 dPQ, dQ, dC, dS;
+    struct Ctx { const float* pix; int p, q; bool ok; };
+    __device__ __forceinline__ Ctx prep(int m) const {
+        const uint32_t img = dPQ.div(m), pq = m - img * HWC;
+        const uint32_t p = dQ.div(pq), q = pq - p * Q;
+        return {x + (size_t)img * C * HWC + (int)p * W + (int)q, (int)p, (int)q, m < M};
+    }
+    __device__ __forceinline__ void row(int kb, const Ctx& t, float (&v)[BK]) const {
+        const uint32_t k0 = (uint32_t)kb * BK;
+        const uint32_t rs = dC.div(k0), c0 = k0 - rs * C;
+        const uint32_t r = dS.div(rs), s = rs - r * S;
+        const int dr = (int)r - pad, ds = (int)s - pad;
+        const bool ok = t.ok && (unsigned)(t.p + dr) < (unsigned)H && (unsigned)(t.q + ds) < (unsigned)W;
+        const float* src = t.pix + ((int)c0 * HWC + dr * W + ds);
+#pragma unroll
+        for (int j = 0; j < BK; ++j) v[j] = ok ? __ldg(src + j * HWC) : 0.f;
+    }
+};
+
 template <int BN, class ALoad, class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
 fwd_bf16_kernel(ALoad A, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_w_lo, Epi epi, int nkb) {
@@ -473,7 +499,25 @@ int tc4_conv_fwd(const float* x, const void* w_hi, const void* w_lo, const float
     const int ld = R * S * C, nkb = ld / BK2;
     const uint16_t* wh = static_cast<const uint16_t*>(w_hi);
     const uint16_t* wl = static_cast<const uint16_t*>(w_lo);
-    if (K % 128 == 0 || K > 64) return launch_fwd<128>(A, wh, wl, K, ld, e, M, nkb, s);
+    const bool wide = (K % 128 == 0 || K > 64);
+    static int hwspec = -1;
+    if (hwspec < 0) { const char* ev = getenv("CLB_BF16_HWSPEC"); hwspec = (ev && ev[0] == '1') ? 1 : 0; }
+    if (hwspec) {
+#define CLB_HW_CASE(HWV)                                                                                              \
+        case HWV: {                                                                                                       \
+            PixelRowsHW<HWV> Ah{x, C, H, W, R, S, pad, P, Q, M, FastDiv32(P * Q), FastDiv32(Q), FastDiv32(C), FastDiv32(S)}; \
+            return wide ? launch_fwd<128>(Ah, wh, wl, K, ld, e, M, nkb, s) : launch_fwd<64>(Ah, wh, wl, K, ld, e, M, nkb, s); \
+        }
+        switch (H * W) {
+            CLB_HW_CASE(16)
+            CLB_HW_CASE(64)
+            CLB_HW_CASE(256)
+            CLB_HW_CASE(1024)
+            default: break;
+        }
+#undef CLB_HW_CASE
+    }
+    if (wide) return launch_fwd<128>(A, wh, wl, K, ld, e, M, nkb, s);
     return launch_fwd<64>(A, wh, wl, K, ld, e, M, nkb, s);
 }
 

@@ -319,6 +319,10 @@ struct TapChunks {
         }
     }
     // shift, split into bf16 hi / lo and store: row r = (tg >> 3) + 16 i, 16-byte chunk (tg & 7) ^ (r & 7)
+    // BRANCHY: the four rows of a warp (consecutive tap rows, C % 4 == 0) share their filter tap, so ds is warp-uniform
+    // and three straight-line variants behind a (non-divergent) branch replace the 16 selects per row; still correct
+    // when rows do straddle taps (the branch then diverges).  Opt-in: CLB_BF16_WGRAD_BRANCHY=1.
+    template <bool BRANCHY>
     __device__ __forceinline__ void store(const Ctx& t, const Regs& g, int tg, uint32_t tile_hi, uint32_t tile_lo) const {
         const int c = tg & 7, r0 = tg >> 3;
         const uint32_t off0 = (uint32_t)r0 * 128u + (uint32_t)((c ^ (r0 & 7)) << 4);
@@ -326,6 +330,22 @@ struct TapChunks {
         for (int i = 0; i < 8; ++i) {
             const float v[8] = {g.a[i].x, g.a[i].y, g.a[i].z, g.a[i].w, g.b[i].x, g.b[i].y, g.b[i].z, g.b[i].w};
             const int ds = t.ds[i];
+            if (BRANCHY) {
+                uint32_t h[4], l[4];
+                if (ds < 0) {
+                    split_pair(g.nb[i], v[0], h[0], l[0]); split_pair(v[1], v[2], h[1], l[1]);
+                    split_pair(v[3], v[4], h[2], l[2]);    split_pair(v[5], v[6], h[3], l[3]);
+                } else if (ds > 0) {
+                    split_pair(v[1], v[2], h[0], l[0]);    split_pair(v[3], v[4], h[1], l[1]);
+                    split_pair(v[5], v[6], h[2], l[2]);    split_pair(v[7], g.nb[i], h[3], l[3]);
+                } else {
+                    split_pair(v[0], v[1], h[0], l[0]);    split_pair(v[2], v[3], h[1], l[1]);
+                    split_pair(v[4], v[5], h[2], l[2]);    split_pair(v[6], v[7], h[3], l[3]);
+                }
+                st_shared_v4(tile_hi + off0 + (uint32_t)i * 2048u, h[0], h[1], h[2], h[3]);
+                st_shared_v4(tile_lo + off0 + (uint32_t)i * 2048u, l[0], l[1], l[2], l[3]);
+                continue;
+            }
             float u[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -341,6 +361,7 @@ struct TapChunks {
     }
 };
 
+template <bool BRANCHY>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_bf16_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_dy_lo,
                   TapChunks B, clb::tcl::EpiSplitK epi, int kb_per_img, int num_kb_total, int kb_per_split) {
@@ -381,7 +402,7 @@ wgrad_bf16_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
             const int s = i % kWgStages;
             mbar_wait(empty + 8 * s, (((uint32_t)(i / kWgStages)) & 1u) ^ 1u);
             const uint32_t st = base + (uint32_t)s * kWgStage;
-            B.store(bctx, g, tg, st + 2 * kTile, st + 3 * kTile);
+            B.template store<BRANCHY>(bctx, g, tg, st + 2 * kTile, st + 3 * kTile);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(b_full + 8 * s);
@@ -480,9 +501,16 @@ int tc4_conv_wgrad(const float* x, const float* dy, float* ws_partials, float* b
     TapChunks B{x, C, H, W, R, S, pad, n_rows, npix, FastDiv32(PQ), FastDiv32(W), FastDiv32(C), FastDiv32(S)};
     clb::tcl::EpiSplitK e{ws_partials, K, n_rows, (int64_t)K * n_rows};
     dim3 grid((K + BM - 1) / BM, (n_rows + 127) / 128, splits);
-    static bool configured = false;
-    if (!configured) { CLB_CUDA(cudaFuncSetAttribute(wgrad_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem)); configured = true; }
-    wgrad_bf16_kernel<<<grid, kWgThreads, kWgSmem, s>>>(m_hi, m_lo, B, e, PQ / BK2, nkb, per); clb::count_launch();
+    static int branchy = -1;
+    if (branchy < 0) { const char* ev = getenv("CLB_BF16_WGRAD_BRANCHY"); branchy = (ev && ev[0] == '1') ? 1 : 0; }
+    static bool configured[2] = {false, false};
+    if (branchy) {
+        if (!configured[1]) { CLB_CUDA(cudaFuncSetAttribute(wgrad_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem)); configured[1] = true; }
+        wgrad_bf16_kernel<true><<<grid, kWgThreads, kWgSmem, s>>>(m_hi, m_lo, B, e, PQ / BK2, nkb, per); clb::count_launch();
+    } else {
+        if (!configured[0]) { CLB_CUDA(cudaFuncSetAttribute(wgrad_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem)); configured[0] = true; }
+        wgrad_bf16_kernel<false><<<grid, kWgThreads, kWgSmem, s>>>(m_hi, m_lo, B, e, PQ / BK2, nkb, per); clb::count_launch();
+    }
     return CLB_OK;
 }
 

@@ -14,6 +14,7 @@ from the reference's own functions, imported through oracle/refshim.py:
              update_reg_params}                                            (a10-a12)
   gem      : methods.rehearsal.model.gem.Net.observe                       (a13-a16)
   qp       : known-answer vectors for project2cone2's QP (oracle/qp.py, cross-checked with scipy)
+  ragged   : finetune / EWC / MAS again with dataset sizes that leave ragged last batches (56, 41, 18 at bs 16)
 
 Inputs are synthetic (torch.Generator seeds recorded in each fixture), the seed protocol is the
 reference's utils.set_random(7).  The model is a reference VGGSlim with a small extra config
@@ -229,6 +230,64 @@ def gen_gem(tmp):
     torch.save(out, os.path.join(GOLDEN, "gem.pt"))
 
 
+def gen_ragged(tmp):
+    """Ragged tails: a 56-image importance pass (batches 16,16,16,8 -- MAS's running average uses the
+    CURRENT batch size, train_MAS.py:168-173), training on 41 images (16,16,9) and validation on 18 (16,2)."""
+    import torch.optim as optim
+    import methods.Finetune.train_SGD as TS
+    n_prev, n_train, n_val = 56, 41, 18
+    out = {}
+
+    def ragged_loaders(seed):
+        xt, yt = make_task(seed, n_train)
+        xv, yv = make_task(seed + 1000, n_val)
+        mk = lambda x, y: torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=BS, shuffle=False)
+        return {"train": mk(xt, yt), "val": mk(xv, yv)}, {"train": n_train, "val": n_val}, (xt, yt, xv, yv)
+
+    model = new_model()
+    init = sd(model)
+    loaders, sizes, data = ragged_loaders(51)
+    crit = RecCE()
+    opt = optim.SGD(model.parameters(), 0.05, momentum=0.9, weight_decay=5e-4)
+    with quiet():
+        model, best = TS.train_model(model, crit, opt, 0.05, loaders, sizes, False, 2, exp_dir=tmp, resume="",
+                                     save_models_mode=False)
+    out["finetune"] = dict(init=init, final=sd(model), best_acc=float(best), losses=crit.losses, lr=0.05, wd=5e-4,
+                           epochs=2, data=data)
+    for which in ("ewc", "mas"):
+        if which == "ewc":
+            import methods.EWC.main_EWC as M
+            import methods.EWC.train_EWC as T
+            accumulate = lambda model, path: M.accumulate_EWC_weights(None, [path], model, BS)
+        else:
+            import methods.MAS.main_MAS as M
+            import methods.MAS.train_MAS as T
+            accumulate = lambda model, path: M.accumulate_objective_based_weights(None, [path], model, BS, "L2",
+                                                                                   test_set="train")
+        model = new_model()
+        init = sd(model)
+        lam = 50.0 if which == "ewc" else 3.0
+        xp, yp = make_task(61, n_prev)
+        dpath = os.path.join(tmp, "%s_ragged_prev.pth" % which)
+        save_dsets(dpath, xp, yp)
+        with quiet():
+            model = accumulate(model, dpath)
+        model.reg_params["lambda"] = lam
+        reg_after_pass = reg_dump(model, ("omega", "init_val"))
+        torch.manual_seed(300)
+        model.classifier._modules["4"] = nn.Linear(32, NCLS)
+        head = {k: v.clone() for k, v in model.classifier._modules["4"].state_dict().items()}
+        loaders, sizes, data = ragged_loaders(62)
+        crit = RecCE()
+        opt = T.Weight_Regularized_SGD(model.parameters(), 0.05, momentum=0.9, weight_decay=0.0)
+        with quiet():
+            model, best = T.train_model(model, crit, opt, 0.05, loaders, sizes, False, 2, exp_dir=tmp + "/", resume="")
+        out[which] = dict(init=init, prev_data=(xp, yp), data=data, lam=lam, lr=0.05, wd=0.0, epochs=2,
+                          reg_after_pass=reg_after_pass, new_head=head, final=sd(model), best_acc=float(best),
+                          losses=crit.losses)
+    torch.save(out, os.path.join(GOLDEN, "ragged.pt"))
+
+
 def gen_qp():
     import scipy.optimize as so
     from oracle import qp
@@ -258,7 +317,13 @@ def main():
     refshim.install()
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(1)                                # fixed reduction order for the fixtures
+    if len(sys.argv) > 1 and sys.argv[1] == "ragged":       # add the ragged-tail fixture without touching the others
+        with tempfile.TemporaryDirectory() as tmp:
+            gen_ragged(tmp)
+        print("ragged.pt", os.path.getsize(os.path.join(GOLDEN, "ragged.pt")))
+        return
     with tempfile.TemporaryDirectory() as tmp:
+        gen_ragged(tmp)
         gen_finetune(tmp)
         _penalty_method(tmp, "ewc")
         _penalty_method(tmp, "mas")

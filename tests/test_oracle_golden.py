@@ -143,3 +143,41 @@ def test_qp_known_answers():
         v64 = qp.solve_lower_bounded_qp(Pm, -(M @ gvec), np.full(k, c["margin"]))
         assert np.abs(v64 - c["v"].numpy()).max() <= 1e-9 * max(1.0, np.abs(v64).max())
         assert (v64 >= c["margin"] - 1e-9).all()
+
+
+def test_ragged_tails_match_reference():
+    """Ragged last batches (56 = 16+16+16+8 importance images, 41 = 16+16+9 training, 18 = 16+2 validation): MAS's running
+    average divides by the CURRENT batch size (train_MAS.py:168-173), mean-CE of a short batch, epoch statistics."""
+    g = load_golden("ragged")
+    f = g["finetune"]
+    m = tiny_model(f["init"])
+    ld, sizes = loaders(f["data"])
+    tr = restate.Trainer(m, "sgd", f["lr"], wd=f["wd"])
+    best, _, _ = tr.train_model(ld, sizes, f["epochs"])
+    assert abs(best - f["best_acc"]) < 1e-12
+    nb_t, nb_v = len(ld["train"]), len(ld["val"])
+    assert (nb_t, nb_v) == (3, 2)
+    ref = [l for e in range(f["epochs"]) for l in f["losses"][e * (nb_t + nb_v): e * (nb_t + nb_v) + nb_t]]
+    assert np.allclose(tr.batch_losses, ref, rtol=1e-6, atol=0)
+    for k, v in f["final"].items():
+        assert rel_err(m.state_dict()[k], v) <= TOL, k
+    for which in ("ewc", "mas"):
+        r = g[which]
+        m = tiny_model(r["init"])
+        xp, yp = r["prev_data"]
+        bl = batches(xp, yp)
+        assert [len(b[0]) for b in bl] == [16, 16, 16, 8]
+        om = restate.fisher_pass(m, bl, len(xp)) if which == "ewc" else restate.mas_pass(m, bl)
+        names = [n for n, _ in m.named_parameters()]
+        for n, o, p in zip(names, om, m.parameters()):
+            assert rel_err(o, r["reg_after_pass"][n]["omega"]) <= TOL, (which, n)
+            assert rel_err(p.data, r["reg_after_pass"][n]["init_val"]) <= TOL
+        reg = [dict(omega=o.clone(), init_val=p.data.clone()) for o, p in zip(om, m.parameters())]
+        m.classifier._modules["4"].load_state_dict(r["new_head"])
+        reg[-1] = reg[-2] = None
+        ld, sizes = loaders(r["data"])
+        tr = restate.Trainer(m, "penalty", r["lr"], reg=reg, lam=r["lam"], wd=r["wd"])
+        best, _, _ = tr.train_model(ld, sizes, r["epochs"])
+        assert abs(best - r["best_acc"]) < 1e-12
+        for k, v in r["final"].items():
+            assert rel_err(m.state_dict()[k], v) <= TOL, (which, k)

@@ -22,7 +22,9 @@ def compute_importance_l2(model, optimizer, lr_scheduler, dset_loaders, use_gpu)
     """train_MAS.py:508-567: per batch L = sum(out**2), backward, omega <- (omega*b*n_b + |g|)/((b+1)*n_b).
 
     Data parallel: whole batches are dealt round-robin; each rank accumulates sum_b |g_b| (prev=1, curr=1 form) and the
-    all-reduced sum is divided once -- equal to the reference's running mean for equal batch sizes."""
+    all-reduced sum is divided once -- equal to the reference's running mean for equal batch sizes.
+    (The recurrence unrolls to omega = mean_b(|g_b| / n_b), so ragged batches could be sharded too by accumulating
+    |g_b| / n_b per batch; the sharded path currently insists on equal batch sizes -- the BASELINE configs have them.)"""
     eng = engine_of(model.parameters())
     model.eval()
     world, rk = cdist.world_size(), cdist.rank()

@@ -15,6 +15,7 @@ from the reference's own functions, imported through oracle/refshim.py:
   gem      : methods.rehearsal.model.gem.Net.observe                       (a13-a16)
   qp       : known-answer vectors for project2cone2's QP (oracle/qp.py, cross-checked with scipy)
   ragged   : finetune / EWC / MAS again with dataset sizes that leave ragged last batches (56, 41, 18 at bs 16)
+  imm      : methods.IMM.merge.{diag_fisher, IMM_merge_models} (mode-IMM precision with sampled labels, mean / mode merge)
 
 Inputs are synthetic (torch.Generator seeds recorded in each fixture), the seed protocol is the
 reference's utils.set_random(7).  The model is a reference VGGSlim with a small extra config
@@ -288,6 +289,46 @@ def gen_ragged(tmp):
     torch.save(out, os.path.join(GOLDEN, "ragged.pt"))
 
 
+def gen_imm(tmp):
+    """IMM (groundwork for the next row): mode-IMM precision = methods.IMM.merge.diag_fisher (labels SAMPLED
+    from the model's own softmax with torch.multinomial, mean NLL per batch, divisor = number of BATCHES of the phase,
+    merge.py:155-186) and the mean / mode merges (merge.py:188-242) over three task models."""
+    import methods.IMM.merge as MG
+    models, datas = [], []
+    for t in range(3):
+        m = new_model()
+        g = torch.Generator().manual_seed(400 + t)
+        with torch.no_grad():
+            for p in m.parameters():                       # three different "trained" models of the same architecture
+                p.add_(torch.randn(p.shape, generator=g) * 0.05)
+        models.append(m)
+        datas.append((make_task(410 + t, 40), make_task(420 + t, 24)))
+    head_names = ["classifier.4.weight", "classifier.4.bias"]
+    precisions, seeds = [], []
+    for t, m in enumerate(models):
+        (xt, yt), (xv, yv) = datas[t]
+        mk = lambda x, y: torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=BS, shuffle=False)
+        m.params = {n: p for n, p in m.named_parameters() if p.requires_grad}
+        torch.manual_seed(430 + t)                         # the multinomial draws come from the global CPU generator
+        seeds.append(430 + t)
+        with quiet():
+            prec = MG.diag_fisher(m, {"train": mk(xt, yt), "val": mk(xv, yv)}, exclude_params=head_names)
+        precisions.append({n: v.detach().clone() for n, v in prec.items()})
+        del m.params
+    sums = [precisions[0]]
+    for t in range(1, 3):
+        sums.append({n: sums[-1][n] + precisions[t][n] for n in precisions[t]})
+    merged_mean, merged_mode = [], []
+    for idx in (1, 2):
+        with quiet():
+            mm = MG.IMM_merge_models(models, idx, head_names, mean_mode=True)
+            md = MG.IMM_merge_models(models, idx, head_names, precision=precisions, sum_precision=sums[idx], mean_mode=False)
+        merged_mean.append(sd(mm))
+        merged_mode.append(sd(md))
+    torch.save(dict(states=[sd(m) for m in models], data=datas, seeds=seeds, head_names=head_names, precisions=precisions,
+                    merged_mean=merged_mean, merged_mode=merged_mode), os.path.join(GOLDEN, "imm.pt"))
+
+
 def gen_qp():
     import scipy.optimize as so
     from oracle import qp
@@ -317,13 +358,14 @@ def main():
     refshim.install()
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(1)                                # fixed reduction order for the fixtures
-    if len(sys.argv) > 1 and sys.argv[1] == "ragged":       # add the ragged-tail fixture without touching the others
+    if len(sys.argv) > 1 and sys.argv[1] in ("ragged", "imm"):   # add one fixture without touching the others
         with tempfile.TemporaryDirectory() as tmp:
-            gen_ragged(tmp)
-        print("ragged.pt", os.path.getsize(os.path.join(GOLDEN, "ragged.pt")))
+            (gen_ragged if sys.argv[1] == "ragged" else gen_imm)(tmp)
+        print(sys.argv[1] + ".pt", os.path.getsize(os.path.join(GOLDEN, sys.argv[1] + ".pt")))
         return
     with tempfile.TemporaryDirectory() as tmp:
         gen_ragged(tmp)
+        gen_imm(tmp)
         gen_finetune(tmp)
         _penalty_method(tmp, "ewc")
         _penalty_method(tmp, "mas")

@@ -134,6 +134,53 @@ def mas_pass(model, batches):
     return omega
 
 
+def imm_precision_pass(model, phase_batches, exclude_names):
+    """mode-IMM precision, methods/IMM/merge.py:155-186: starts at 1e-8; eval mode; for every phase and
+    batch: targets ~ multinomial(softmax(out)) drawn from the GLOBAL torch generator, L = MEAN NLL of the sampled targets,
+    precision += grad**2 / (number of BATCHES of that phase).  phase_batches: {phase: [(x, y), ...]} in the reference's
+    dict order.  Returns {name: tensor} without the head parameters."""
+    model.eval()
+    names = [n for n, _ in model.named_parameters()]
+    prec = {n: torch.zeros_like(p) + 1e-8 for n, p in model.named_parameters() if n not in exclude_names}
+    for phase, batches in phase_batches.items():
+        # the reference iterates a DataLoader per phase; creating its iterator draws one int64 (the workers' base seed)
+        # from the global generator, which shifts the multinomial stream that follows
+        torch.empty((), dtype=torch.int64).random_()
+        for x, _ in batches:
+            out = model(x)
+            targets = torch.multinomial(torch.softmax(out, dim=1).detach(), 1).squeeze()
+            loss = torch.nn.functional.nll_loss(torch.log_softmax(out, dim=1), targets, reduction="mean")
+            g = grads_of(model, loss)
+            for n, gi in zip(names, g):
+                if n in prec:
+                    prec[n] += gi ** 2 / len(batches)
+    return prec
+
+
+def imm_merge(states, upto, head_names, precisions=None, sum_precision=None, as_reference=True):
+    """IMM_merge_models (merge.py:188-242): the state of task `upto` with every non-head parameter replaced by
+    sum_k precision_k / sum_precision * theta_k (mode-IMM) or -- as intended -- by the mean over tasks 0..upto (mean-IMM).
+
+    Reference quirk (pinned by tests/golden/imm.pt): in mean mode the loop re-binds `param_value` to a state_dict tensor
+    of the last merged-in model (merge.py:225-226), so the final `param_value.data = mean_param.clone()` (merge.py:239)
+    lands on that temporary and the returned model is an UNCHANGED copy of task `upto`'s model.  as_reference=True
+    reproduces that; as_reference=False computes the intended mean."""
+    merged = {k: v.clone() for k, v in states[upto].items()}
+    if precisions is None and as_reference:
+        return merged
+    for name in states[upto]:
+        if name in head_names:
+            continue
+        acc = torch.zeros_like(states[upto][name])
+        for k in range(upto + 1):
+            if precisions is None:
+                acc = acc + states[k][name]
+            else:
+                acc += (precisions[k][name] / sum_precision[name]) * states[k][name]
+        merged[name] = acc / (upto + 1) if precisions is None else acc
+    return merged
+
+
 def accumulate_protocol(prev_omega, new_omega):
     """store_prev / accumelate_reg_params (EWC/main_EWC.py:177-232, MAS/train_MAS.py:710-795): omega = prev + new."""
     return [a + b for a, b in zip(prev_omega, new_omega)]

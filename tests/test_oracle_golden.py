@@ -181,3 +181,32 @@ def test_ragged_tails_match_reference():
         assert abs(best - r["best_acc"]) < 1e-12
         for k, v in r["final"].items():
             assert rel_err(m.state_dict()[k], v) <= TOL, (which, k)
+
+
+def test_imm_precision_and_merges_match_reference():
+    """Groundwork for SURVEY 8f-3: mode-IMM precision (sampled labels; divisor = #batches of the phase) and the mean /
+    mode merges of three task models against methods/IMM/merge.py run unmodified."""
+    g = load_golden("imm")
+    precisions = []
+    for t, state in enumerate(g["states"]):
+        m = tiny_model(state)
+        (xt, yt), (xv, yv) = g["data"][t]
+        torch.manual_seed(g["seeds"][t])
+        prec = restate.imm_precision_pass(m, {"train": batches(xt, yt), "val": batches(xv, yv)}, g["head_names"])
+        assert set(prec) == set(g["precisions"][t])
+        for n, v in g["precisions"][t].items():
+            assert rel_err(prec[n], v) <= TOL, (t, n)
+        precisions.append(prec)
+    sums = [precisions[0]]
+    for t in (1, 2):
+        sums.append({n: sums[-1][n] + precisions[t][n] for n in precisions[t]})
+    for i, upto in enumerate((1, 2)):
+        mean = restate.imm_merge(g["states"], upto, g["head_names"])
+        mode = restate.imm_merge(g["states"], upto, g["head_names"], precisions, sums[upto])
+        intended = restate.imm_merge(g["states"], upto, g["head_names"], as_reference=False)
+        for k in g["merged_mean"][i]:
+            assert torch.equal(mean[k], g["merged_mean"][i][k]), ("mean", upto, k)      # the reference's no-op (see restate)
+            assert rel_err(mode[k], g["merged_mode"][i][k]) <= TOL, ("mode", upto, k)
+        k = "features.0.weight"
+        assert rel_err(intended[k], sum(g["states"][j][k] for j in range(upto + 1)) / (upto + 1)) <= 1e-6
+        assert not torch.equal(intended[k], mean[k])

@@ -15,6 +15,7 @@ from the reference's own functions, imported through oracle/refshim.py:
   gem      : methods.rehearsal.model.gem.Net.observe                       (a13-a16)
   qp       : known-answer vectors for project2cone2's QP (oracle/qp.py, cross-checked with scipy)
   ragged   : finetune / EWC / MAS again with dataset sizes that leave ragged last batches (56, 41, 18 at bs 16)
+  schedule : the epoch protocol over 30 epochs without improvement (lr cut at count 5, stop at > 10; SI: >= 10)
   imm      : methods.IMM.merge.{diag_fisher, IMM_merge_models} (mode-IMM precision with sampled labels, mean / mode merge)
 
 Inputs are synthetic (torch.Generator seeds recorded in each fixture), the seed protocol is the
@@ -329,6 +330,44 @@ def gen_imm(tmp):
                     merged_mean=merged_mean, merged_mode=merged_mode), os.path.join(GOLDEN, "imm.pt"))
 
 
+def gen_schedule(tmp):
+    """The epoch protocol over a LONG run (A.1): with lr = 1e-9 nothing improves after the first validation, so
+    val_beat_counts climbs 1, 2, ...; lr is cut at count == 5 and training stops at count > 10 (Finetune / EWC / MAS)
+    resp. count >= 10 (SI, whose epoch range is also num_epochs + 1).  Recorded: criterion calls (= batches processed,
+    i.e. how many epochs actually ran), the optimiser's final lr, best accuracy."""
+    import torch.optim as optim
+    import methods.Finetune.train_SGD as TS
+    import methods.EWC.train_EWC as TE
+    import methods.SI.train_SI as TI
+    out = {}
+    for which in ("sgd", "ewc", "si", "sgd_short"):
+        model = new_model()
+        init = sd(model)
+        loaders, sizes, data = loaders_for(71)
+        crit = RecCE()
+        lr0, epochs = 1e-9, (8 if which == "sgd_short" else 30)
+        with quiet():
+            if which.startswith("sgd"):
+                opt = optim.SGD(model.parameters(), lr0, momentum=0.9, weight_decay=0.0)
+                model, best = TS.train_model(model, crit, opt, lr0, loaders, sizes, False, epochs, exp_dir=tmp, resume="",
+                                             save_models_mode=False)
+            elif which == "ewc":
+                model.reg_params = {p: dict(omega=torch.ones_like(p), init_val=p.data.clone()) for p in model.parameters()}
+                model.reg_params["lambda"] = 1.0
+                opt = TE.Weight_Regularized_SGD(model.parameters(), lr0, momentum=0.9, weight_decay=0.0)
+                model, best = TE.train_model(model, crit, opt, lr0, loaders, sizes, False, epochs, exp_dir=tmp + "/", resume="")
+            else:
+                reg = TI.initialize_reg_params(model)
+                reg["lambda"] = 1.0
+                model.reg_params = reg
+                opt = TI.Elastic_SGD(model.parameters(), lr0, momentum=0.9, weight_decay=0.0)
+                model, best = TI.train_model(model, crit, opt, lr0, loaders, sizes, False, epochs, exp_dir=tmp + "/", resume="")
+        out["init"], out["data"] = init, data                 # identical for the four runs (same seeds)
+        out[which] = dict(lr=lr0, epochs=epochs, n_criterion_calls=len(crit.losses),
+                          final_lr=float(opt.param_groups[0]["lr"]), best_acc=float(best))
+    torch.save(out, os.path.join(GOLDEN, "schedule.pt"))
+
+
 def gen_qp():
     import scipy.optimize as so
     from oracle import qp
@@ -358,14 +397,15 @@ def main():
     refshim.install()
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(1)                                # fixed reduction order for the fixtures
-    if len(sys.argv) > 1 and sys.argv[1] in ("ragged", "imm"):   # add one fixture without touching the others
+    if len(sys.argv) > 1 and sys.argv[1] in ("ragged", "imm", "schedule"):   # add one fixture without touching the others
         with tempfile.TemporaryDirectory() as tmp:
-            (gen_ragged if sys.argv[1] == "ragged" else gen_imm)(tmp)
+            {"ragged": gen_ragged, "imm": gen_imm, "schedule": gen_schedule}[sys.argv[1]](tmp)
         print(sys.argv[1] + ".pt", os.path.getsize(os.path.join(GOLDEN, sys.argv[1] + ".pt")))
         return
     with tempfile.TemporaryDirectory() as tmp:
         gen_ragged(tmp)
         gen_imm(tmp)
+        gen_schedule(tmp)
         gen_finetune(tmp)
         _penalty_method(tmp, "ewc")
         _penalty_method(tmp, "mas")

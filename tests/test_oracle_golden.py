@@ -210,3 +210,26 @@ def test_imm_precision_and_merges_match_reference():
         k = "features.0.weight"
         assert rel_err(intended[k], sum(g["states"][j][k] for j in range(upto + 1)) / (upto + 1)) <= 1e-6
         assert not torch.equal(intended[k], mean[k])
+
+
+def test_long_run_epoch_protocol_matches_reference():
+    """lr cut at val_beat_counts == 5, stop at > 10 (SI: >= 10, epoch range num_epochs + 1): number of batches processed,
+    final lr and best accuracy of 30-epoch runs of the reference's train_model with a vanishing learning rate."""
+    g = load_golden("schedule")
+    ld, sizes = loaders(g["data"])
+    per_epoch = len(ld["train"]) + len(ld["val"])
+    for which, kind in (("sgd", "sgd"), ("ewc", "penalty"), ("si", "si"), ("sgd_short", "sgd")):
+        r = g[which]
+        m = tiny_model(g["init"])
+        reg = None
+        if kind != "sgd":
+            reg = [dict(omega=torch.ones_like(p) if kind == "penalty" else torch.zeros_like(p), init_val=p.data.clone(),
+                        w=torch.zeros_like(p)) for p in m.parameters()]
+        tr = restate.Trainer(m, kind, r["lr"], reg=reg, lam=1.0)
+        best, log, _ = tr.train_model(ld, sizes, r["epochs"])
+        n_calls = sum(len(ld[phase]) for _, phase, _, _ in log)
+        assert n_calls == r["n_criterion_calls"], (which, n_calls, r["n_criterion_calls"])
+        assert n_calls % per_epoch == 0
+        assert abs(tr.lr - r["final_lr"]) <= 1e-12 * r["final_lr"], (which, tr.lr, r["final_lr"])
+        assert abs(best - r["best_acc"]) < 1e-12
+    assert g["sgd"]["n_criterion_calls"] == 12 * per_epoch and g["si"]["n_criterion_calls"] == 11 * per_epoch

@@ -1,5 +1,5 @@
-"""GPU: the ragged-tail golden fixture (tests/golden/ragged.pt, written at the end of round 1 after the GPU budget was
-spent) through the reference-named entry points.  Run once on a B200 (`python tools/ragged_parity.py`), then move the
+"""GPU: the ragged-tail and long-schedule golden fixtures (tests/golden/{ragged,schedule}.pt, written at the end of round 1
+after the GPU budget was spent) through the reference-named entry points.  Run once on a B200 (`python tools/ragged_parity.py`), then move the
 body into tests/test_gpu_golden.py::test_ragged_tails -- it mirrors test_finetune_train_model / _penalty there."""
 import os, sys, tempfile
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -67,4 +67,34 @@ for which in ("ewc", "mas"):
     for k, v in r["final"].items():
         assert rel_err(m.state_dict()[k], v) <= TOL, (which, k)
     print(which, "ragged ok")
+# ---- long-run epoch protocol (tests/golden/schedule.pt): lr cut at count 5, stop at > 10 (SI >= 10)
+from clsurvey_b200.methods.EWC import train_EWC as TE
+from clsurvey_b200.methods.SI import train_SI as TI
+sch = load_golden("schedule")
+ld, sizes = loaders(sch["data"])
+per_epoch = len(ld["train"]) + len(ld["val"])
+for which in ("sgd", "ewc", "si", "sgd_short"):
+    r = sch[which]
+    m = tiny_model(sch["init"])
+    get_engine(m, (3, 16, 16), BS)
+    if which.startswith("sgd"):
+        opt = SGD(m.parameters(), r["lr"], momentum=0.9, weight_decay=0.0)
+        m, best = train_SGD.train_model(m, nn.CrossEntropyLoss(), opt, r["lr"], ld, sizes, True, r["epochs"], exp_dir=tmp,
+                                        resume="", save_models_mode=False)
+    elif which == "ewc":
+        m.reg_params = {p: dict(omega=torch.ones_like(p), init_val=p.data.clone()) for p in m.parameters()}
+        m.reg_params["lambda"] = 1.0
+        opt = TE.Weight_Regularized_SGD(m.parameters(), r["lr"], momentum=0.9, weight_decay=0.0)
+        m, best = TE.train_model(m, nn.CrossEntropyLoss(), opt, r["lr"], ld, sizes, True, r["epochs"], exp_dir=tmp, resume="")
+    else:
+        reg = TI.initialize_reg_params(m)
+        reg["lambda"] = 1.0
+        m.reg_params = reg
+        opt = TI.Elastic_SGD(m.parameters(), r["lr"], momentum=0.9, weight_decay=0.0)
+        m, best = TI.train_model(m, nn.CrossEntropyLoss(), opt, r["lr"], ld, sizes, True, r["epochs"], exp_dir=tmp, resume="")
+    n_calls = sum(len(ld[phase]) for _, phase, _, _ in trainers.LAST_RUN["epochs"])
+    assert n_calls == r["n_criterion_calls"], (which, n_calls, r["n_criterion_calls"])
+    assert abs(opt.param_groups[0]["lr"] - r["final_lr"]) <= 1e-12 * r["final_lr"], (which, opt.param_groups[0]["lr"])
+    assert best == r["best_acc"], (which, best, r["best_acc"])
+    print(which, "schedule ok:", n_calls // per_epoch, "epochs")
 print("RAGGED_PARITY_OK")

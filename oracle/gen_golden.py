@@ -362,9 +362,34 @@ def gen_schedule(tmp):
                 model.reg_params = reg
                 opt = TI.Elastic_SGD(model.parameters(), lr0, momentum=0.9, weight_decay=0.0)
                 model, best = TI.train_model(model, crit, opt, lr0, loaders, sizes, False, epochs, exp_dir=tmp + "/", resume="")
-        out["init"], out["data"] = init, data                 # identical for the four runs (same seeds)
+        out["init"], out["data"] = init, data                 # identical for all runs (same seeds)
         out[which] = dict(lr=lr0, epochs=epochs, n_criterion_calls=len(crit.losses),
                           final_lr=float(opt.param_groups[0]["lr"]), best_acc=float(best))
+    # divergence: EWC / MAS / SI abort the run when the epoch loss exceeds 1e4 or is NaN (train_EWC.py:204-205,
+    # train_SI.py:242-244); Finetune has no such check (train_SGD.py) and keeps going
+    for which in ("diverge_ewc", "diverge_si", "diverge_sgd"):
+        model = new_model()
+        loaders, sizes, data = loaders_for(71)
+        crit = RecCE()
+        lr0, epochs = 1e3, 4
+        with quiet():
+            if which == "diverge_sgd":
+                opt = optim.SGD(model.parameters(), lr0, momentum=0.9, weight_decay=0.0)
+                model, best = TS.train_model(model, crit, opt, lr0, loaders, sizes, False, epochs, exp_dir=tmp, resume="",
+                                             save_models_mode=False)
+            elif which == "diverge_ewc":
+                model.reg_params = {p: dict(omega=torch.ones_like(p), init_val=p.data.clone()) for p in model.parameters()}
+                model.reg_params["lambda"] = 1.0
+                opt = TE.Weight_Regularized_SGD(model.parameters(), lr0, momentum=0.9, weight_decay=0.0)
+                model, best = TE.train_model(model, crit, opt, lr0, loaders, sizes, False, epochs, exp_dir=tmp + "/", resume="")
+            else:
+                reg = TI.initialize_reg_params(model)
+                reg["lambda"] = 1.0
+                model.reg_params = reg
+                opt = TI.Elastic_SGD(model.parameters(), lr0, momentum=0.9, weight_decay=0.0)
+                model, best = TI.train_model(model, crit, opt, lr0, loaders, sizes, False, epochs, exp_dir=tmp + "/", resume="")
+        out[which] = dict(lr=lr0, epochs=epochs, n_criterion_calls=len(crit.losses), best_acc=float(best),
+                          final_lr=float(opt.param_groups[0]["lr"]))
     torch.save(out, os.path.join(GOLDEN, "schedule.pt"))
 
 

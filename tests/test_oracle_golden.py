@@ -233,3 +233,17 @@ def test_long_run_epoch_protocol_matches_reference():
         assert abs(tr.lr - r["final_lr"]) <= 1e-12 * r["final_lr"], (which, tr.lr, r["final_lr"])
         assert abs(best - r["best_acc"]) < 1e-12
     assert g["sgd"]["n_criterion_calls"] == 12 * per_epoch and g["si"]["n_criterion_calls"] == 11 * per_epoch
+    # divergence (lr = 1e3): EWC / SI abort after the first training phase (epoch loss > 1e4 or NaN), Finetune carries on
+    for which, kind in (("diverge_ewc", "penalty"), ("diverge_si", "si"), ("diverge_sgd", "sgd")):
+        r = g[which]
+        m = tiny_model(g["init"])
+        reg = None
+        if kind != "sgd":
+            reg = [dict(omega=torch.ones_like(p) if kind == "penalty" else torch.zeros_like(p), init_val=p.data.clone(),
+                        w=torch.zeros_like(p)) for p in m.parameters()]
+        tr = restate.Trainer(m, kind, r["lr"], reg=reg, lam=1.0)
+        best, log, _ = tr.train_model(ld, sizes, r["epochs"])
+        n_calls = sum(len(ld[phase]) for _, phase, _, _ in log)
+        assert n_calls == r["n_criterion_calls"], (which, n_calls, r["n_criterion_calls"])
+        assert abs(best - r["best_acc"]) < 1e-12, (which, best, r["best_acc"])
+    assert g["diverge_ewc"]["n_criterion_calls"] == len(ld["train"]) and g["diverge_sgd"]["n_criterion_calls"] == 4 * per_epoch

@@ -73,15 +73,15 @@ from clsurvey_b200.methods.SI import train_SI as TI
 sch = load_golden("schedule")
 ld, sizes = loaders(sch["data"])
 per_epoch = len(ld["train"]) + len(ld["val"])
-for which in ("sgd", "ewc", "si", "sgd_short"):
+for which in ("sgd", "ewc", "si", "sgd_short", "diverge_ewc", "diverge_si", "diverge_sgd"):
     r = sch[which]
     m = tiny_model(sch["init"])
     get_engine(m, (3, 16, 16), BS)
-    if which.startswith("sgd"):
+    if which.endswith("sgd") or which == "sgd_short":
         opt = SGD(m.parameters(), r["lr"], momentum=0.9, weight_decay=0.0)
         m, best = train_SGD.train_model(m, nn.CrossEntropyLoss(), opt, r["lr"], ld, sizes, True, r["epochs"], exp_dir=tmp,
                                         resume="", save_models_mode=False)
-    elif which == "ewc":
+    elif which.endswith("ewc"):
         m.reg_params = {p: dict(omega=torch.ones_like(p), init_val=p.data.clone()) for p in m.parameters()}
         m.reg_params["lambda"] = 1.0
         opt = TE.Weight_Regularized_SGD(m.parameters(), r["lr"], momentum=0.9, weight_decay=0.0)

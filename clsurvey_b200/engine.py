@@ -128,6 +128,7 @@ class Engine:
                 _ENGINES[id(p)] = self
         del old_theta
         self._graphs = {}
+        self._dp_cut_cache = None                     # offsets may have moved (head swap)
         self._compile()
 
     def view(self, flat, i):

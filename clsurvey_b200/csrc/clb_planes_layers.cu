@@ -1,0 +1,306 @@
+// HBM-bound kernels of the "planes" pipeline (NHWC bf16 hi/lo planes): weight re-ordering, 2x2 max-pooling forward /
+// backward (with the layout changes at both ends of the conv stack), bias gradients and the split-K reduction.
+// Replaces nn.MaxPool2d / nn.ReLU backward of src/models/VGGSlim.py:27-40 for the layers that run on the planes kernels.
+#include <float.h>
+
+#include "clb_planes.cuh"
+
+namespace clb {
+namespace pl {
+
+static inline int ew_grid(int64_t n, int threads) {
+    int64_t b = (n + threads - 1) / threads, cap = (int64_t)sm_count() * 16;
+    if (b > cap) b = cap;
+    return (int)(b < 1 ? 1 : b);
+}
+
+// ------------------------------------------------------------------------------------------------ weights -> planes
+// w [K][C][3][3] fp32  ->  wf [K][tap][C] (forward B operand) and wt [C][8 - tap][K] (dgrad B operand: flipped taps,
+// transposed channels), each as bf16 hi / lo planes.  blockIdx.y selects the layout so that the writes of both are coalesced.
+__global__ void __launch_bounds__(256) weights_to_planes_kernel(const float* __restrict__ w, uint16_t* __restrict__ wf_hi,
+                                                                uint16_t* __restrict__ wf_lo, uint16_t* __restrict__ wt_hi,
+                                                                uint16_t* __restrict__ wt_lo, int K, int C) {
+    const int64_t total = (int64_t)K * C, gs = (int64_t)gridDim.x * blockDim.x;
+    const bool dgrad = blockIdx.y == 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gs) {
+        int k, c;
+        if (!dgrad) { k = (int)(i / C); c = (int)(i - (int64_t)k * C); }          // c fastest
+        else { c = (int)(i / K); k = (int)(i - (int64_t)c * K); }                  // k fastest
+        const float* src = w + ((int64_t)k * C + c) * 9;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            uint32_t hi, lo;
+            split1(__ldg(src + t), hi, lo);
+            if (!dgrad) {
+                const int64_t o = ((int64_t)k * 9 + t) * C + c;
+                wf_hi[o] = (uint16_t)hi; wf_lo[o] = (uint16_t)lo;
+            } else {
+                const int64_t o = ((int64_t)c * 9 + (8 - t)) * K + k;
+                wt_hi[o] = (uint16_t)hi; wt_lo[o] = (uint16_t)lo;
+            }
+        }
+    }
+}
+int weights_to_planes(const float* w, uint16_t* wf_hi, uint16_t* wf_lo, uint16_t* wt_hi, uint16_t* wt_lo, int K, int C,
+                      cudaStream_t s) {
+    dim3 grid(ew_grid((int64_t)K * C, 256), wt_hi ? 2 : 1);
+    weights_to_planes_kernel<<<grid, 256, 0, s>>>(w, wf_hi, wf_lo, wt_hi, wt_lo, K, C); clb::count_launch();
+    return CLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ max-pool 2x2 / 2
+// Window scanned row-major with strict '>' so the FIRST maximum wins (ATen semantics, like clb_maxpool_fwd).
+struct U8x8 { uint32_t a, b; };
+
+// planes [N][H][W][C] -> planes [N][H/2][W/2][C] (OUT_NCHW: fp32 [N][C][H/2][W/2], the classifier's flatten order) + argmax
+// [N][H/2][W/2][C] u8.  One thread = 8 channels of one output pixel.
+template <bool OUT_NCHW>
+__global__ void __launch_bounds__(256) pool_planes_fwd_kernel(const uint16_t* __restrict__ x_hi, const uint16_t* __restrict__ x_lo,
+                                                              uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo,
+                                                              float* __restrict__ y_f32, uint8_t* __restrict__ am, int N, int H,
+                                                              int W, int C) {
+    const int PH = H >> 1, PW = W >> 1, C8 = C >> 3;
+    const int64_t total = (int64_t)N * PH * PW * C8, gs = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gs) {
+        const int c8 = (int)(i % C8);
+        const int64_t op = i / C8;                                   // output pixel (n, ph, pw)
+        const int pw = (int)(op % PW), ph = (int)((op / PW) % PH), n = (int)(op / ((int64_t)PW * PH));
+        float best[8];
+        uint32_t bh[8], bl[8], bi[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { best[j] = -FLT_MAX; bh[j] = bl[j] = bi[j] = 0; }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int64_t ip = (((int64_t)n * H + 2 * ph + (t >> 1)) * W + 2 * pw + (t & 1)) * C + c8 * 8;
+            const uint4 h = __ldg(reinterpret_cast<const uint4*>(x_hi + ip)), l = __ldg(reinterpret_cast<const uint4*>(x_lo + ip));
+            const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t hb = (j & 1) ? hw[j >> 1] >> 16 : hw[j >> 1] & 0xFFFFu;
+                const uint32_t lb = (j & 1) ? lw[j >> 1] >> 16 : lw[j >> 1] & 0xFFFFu;
+                const float v = join1(hb, lb);
+                if (v > best[j] || v != v) { best[j] = v; bh[j] = hb; bl[j] = lb; bi[j] = t; }
+            }
+        }
+        const int64_t o = op * C + c8 * 8;
+        if (OUT_NCHW) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y_f32[(((int64_t)n * C + c8 * 8 + j) * PH + ph) * PW + pw] = best[j];
+        } else {
+            *reinterpret_cast<uint4*>(y_hi + o) = make_uint4(bh[0] | (bh[1] << 16), bh[2] | (bh[3] << 16), bh[4] | (bh[5] << 16), bh[6] | (bh[7] << 16));
+            *reinterpret_cast<uint4*>(y_lo + o) = make_uint4(bl[0] | (bl[1] << 16), bl[2] | (bl[3] << 16), bl[4] | (bl[5] << 16), bl[6] | (bl[7] << 16));
+        }
+        *reinterpret_cast<uint2*>(am + o) = make_uint2(bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24),
+                                                        bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24));
+    }
+}
+
+// fp32 NCHW [N][C][H][W] -> planes [N][H/2][W/2][C] + argmax: one CTA = one output row (n, ph) x 64 channels, transposed
+// through shared memory so that reads (along w) and writes (along c) are both coalesced.  First conv layer's output.
+__global__ void __launch_bounds__(256) pool_nchw_to_planes_kernel(const float* __restrict__ x, uint16_t* __restrict__ y_hi,
+                                                                  uint16_t* __restrict__ y_lo, uint8_t* __restrict__ am, int N,
+                                                                  int C, int H, int W) {
+    extern __shared__ float sm[];                                   // [PW][65] values, then [PW][65] arg-max as float bits
+    const int PH = H >> 1, PW = W >> 1;
+    const int cb = blockIdx.y * 64, ph = blockIdx.x % PH, n = blockIdx.x / PH;
+    float* sv = sm;
+    uint32_t* si = reinterpret_cast<uint32_t*>(sm + PW * 65);
+    for (int i = threadIdx.x; i < 64 * PW; i += blockDim.x) {
+        const int pw = i % PW, c = i / PW;
+        const float* src = x + (((int64_t)n * C + cb + c) * H + 2 * ph) * W + 2 * pw;
+        const float2 a = __ldg(reinterpret_cast<const float2*>(src)), b = __ldg(reinterpret_cast<const float2*>(src + W));
+        float best = -FLT_MAX;
+        uint32_t bi = 0;
+        const float v[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if (v[t] > best || v[t] != v[t]) { best = v[t]; bi = t; }
+        sv[pw * 65 + c] = best;
+        si[pw * 65 + c] = bi;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * PW; i += blockDim.x) {
+        const int c = i & 63, pw = i >> 6;
+        uint32_t hi, lo;
+        split1(sv[pw * 65 + c], hi, lo);
+        const int64_t o = (((int64_t)n * PH + ph) * PW + pw) * C + cb + c;
+        y_hi[o] = (uint16_t)hi; y_lo[o] = (uint16_t)lo; am[o] = (uint8_t)si[pw * 65 + c];
+    }
+}
+
+// backward, planes out: dx[n][2ph+r][2pw+s][c] = (argmax == 2r+s && pooled > 0) ? dy[n][ph][pw][c] : 0   (max-pool backward
+// fused with the ReLU mask of the conv in front: pooled > 0 <=> the selected pre-pool activation was > 0).
+// IN_NCHW: dy and the pooled activation are fp32 [N][C][PH][PW] (classifier side), else planes.
+template <bool IN_NCHW>
+__global__ void __launch_bounds__(256) pool_planes_bwd_kernel(const uint16_t* __restrict__ dy_hi, const uint16_t* __restrict__ dy_lo,
+                                                              const float* __restrict__ dy_f32, const uint16_t* __restrict__ pooled_hi,
+                                                              const float* __restrict__ pooled_f32, const uint8_t* __restrict__ am,
+                                                              uint16_t* __restrict__ dx_hi, uint16_t* __restrict__ dx_lo, int N, int H,
+                                                              int W, int C) {
+    const int PH = H >> 1, PW = W >> 1, C8 = C >> 3;
+    const int64_t total = (int64_t)N * PH * PW * C8, gs = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gs) {
+        const int c8 = (int)(i % C8);
+        const int64_t op = i / C8;
+        const int pw = (int)(op % PW), ph = (int)((op / PW) % PH), n = (int)(op / ((int64_t)PW * PH));
+        const int64_t o = op * C + c8 * 8;
+        uint32_t gh[8], gl[8], idx[8];
+        const uint2 a = __ldg(reinterpret_cast<const uint2*>(am + o));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) idx[j] = ((j < 4 ? a.x : a.y) >> (8 * (j & 3))) & 0xFFu;
+        if (IN_NCHW) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int64_t q = (((int64_t)n * C + c8 * 8 + j) * PH + ph) * PW + pw;
+                const float g = __ldg(pooled_f32 + q) > 0.f ? __ldg(dy_f32 + q) : 0.f;
+                split1(g, gh[j], gl[j]);
+            }
+        } else {
+            const uint4 h = __ldg(reinterpret_cast<const uint4*>(dy_hi + o)), l = __ldg(reinterpret_cast<const uint4*>(dy_lo + o));
+            const uint4 m = __ldg(reinterpret_cast<const uint4*>(pooled_hi + o));
+            const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w}, mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t mb = (j & 1) ? mw[j >> 1] >> 16 : mw[j >> 1] & 0xFFFFu;
+                const bool on = mb != 0 && mb < 0x8000u;
+                gh[j] = on ? ((j & 1) ? hw[j >> 1] >> 16 : hw[j >> 1] & 0xFFFFu) : 0u;
+                gl[j] = on ? ((j & 1) ? lw[j >> 1] >> 16 : lw[j >> 1] & 0xFFFFu) : 0u;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            uint32_t oh[8], ol[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { oh[j] = idx[j] == (uint32_t)t ? gh[j] : 0u; ol[j] = idx[j] == (uint32_t)t ? gl[j] : 0u; }
+            const int64_t ip = (((int64_t)n * H + 2 * ph + (t >> 1)) * W + 2 * pw + (t & 1)) * C + c8 * 8;
+            *reinterpret_cast<uint4*>(dx_hi + ip) = make_uint4(oh[0] | (oh[1] << 16), oh[2] | (oh[3] << 16), oh[4] | (oh[5] << 16), oh[6] | (oh[7] << 16));
+            *reinterpret_cast<uint4*>(dx_lo + ip) = make_uint4(ol[0] | (ol[1] << 16), ol[2] | (ol[3] << 16), ol[4] | (ol[5] << 16), ol[6] | (ol[7] << 16));
+        }
+    }
+}
+
+// backward, fp32 NCHW out (the first conv layer's dY): one CTA = one pooled row (n, ph) x 64 channels; reads planes along c,
+// writes the two full-resolution rows of every channel along w.
+__global__ void __launch_bounds__(256) pool_planes_bwd_to_nchw_kernel(const uint16_t* __restrict__ dy_hi, const uint16_t* __restrict__ dy_lo,
+                                                                      const uint16_t* __restrict__ pooled_hi, const uint8_t* __restrict__ am,
+                                                                      float* __restrict__ dx, int N, int C, int H, int W) {
+    extern __shared__ float sm[];                                   // [64][2][W + 1]
+    const int PH = H >> 1, PW = W >> 1, ldw = W + 1;
+    const int cb = blockIdx.y * 64, ph = blockIdx.x % PH, n = blockIdx.x / PH;
+    for (int i = threadIdx.x; i < 64 * PW; i += blockDim.x) {
+        const int c = i & 63, pw = i >> 6;
+        const int64_t o = (((int64_t)n * PH + ph) * PW + pw) * C + cb + c;
+        const uint32_t mb = pooled_hi[o];
+        const float g = (mb != 0 && mb < 0x8000u) ? join1(dy_hi[o], dy_lo[o]) : 0.f;
+        const uint32_t idx = am[o];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) sm[(c * 2 + (t >> 1)) * ldw + 2 * pw + (t & 1)] = idx == (uint32_t)t ? g : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 2 * W; i += blockDim.x) {
+        const int w = i % W, r = (i / W) & 1, c = i / (2 * W);
+        dx[(((int64_t)n * C + cb + c) * H + 2 * ph + r) * W + w] = sm[(c * 2 + r) * ldw + w];
+    }
+}
+
+int pool_fwd(const uint16_t* x_hi, const uint16_t* x_lo, uint16_t* y_hi, uint16_t* y_lo, float* y_f32, uint8_t* am, int N, int H,
+             int W, int C, cudaStream_t s) {
+    const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
+    if (y_f32) pool_planes_fwd_kernel<true><<<ew_grid(total, 256), 256, 0, s>>>(x_hi, x_lo, nullptr, nullptr, y_f32, am, N, H, W, C);
+    else pool_planes_fwd_kernel<false><<<ew_grid(total, 256), 256, 0, s>>>(x_hi, x_lo, y_hi, y_lo, nullptr, am, N, H, W, C);
+    clb::count_launch();
+    return CLB_OK;
+}
+int pool_fwd_from_nchw(const float* x, uint16_t* y_hi, uint16_t* y_lo, uint8_t* am, int N, int C, int H, int W, cudaStream_t s) {
+    const size_t smem = (size_t)(W / 2) * 65 * 8;
+    pool_nchw_to_planes_kernel<<<dim3(N * (H / 2), C / 64), 256, smem, s>>>(x, y_hi, y_lo, am, N, C, H, W); clb::count_launch();
+    return CLB_OK;
+}
+int pool_bwd(const uint16_t* dy_hi, const uint16_t* dy_lo, const float* dy_f32, const uint16_t* pooled_hi, const float* pooled_f32,
+             const uint8_t* am, uint16_t* dx_hi, uint16_t* dx_lo, int N, int H, int W, int C, cudaStream_t s) {
+    const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
+    if (dy_f32) pool_planes_bwd_kernel<true><<<ew_grid(total, 256), 256, 0, s>>>(nullptr, nullptr, dy_f32, nullptr, pooled_f32, am, dx_hi, dx_lo, N, H, W, C);
+    else pool_planes_bwd_kernel<false><<<ew_grid(total, 256), 256, 0, s>>>(dy_hi, dy_lo, nullptr, pooled_hi, nullptr, am, dx_hi, dx_lo, N, H, W, C);
+    clb::count_launch();
+    return CLB_OK;
+}
+int pool_bwd_to_nchw(const uint16_t* dy_hi, const uint16_t* dy_lo, const uint16_t* pooled_hi, const uint8_t* am, float* dx, int N,
+                     int C, int H, int W, cudaStream_t s) {
+    const size_t smem = (size_t)64 * 2 * (W + 1) * 4;
+    pool_planes_bwd_to_nchw_kernel<<<dim3(N * (H / 2), C / 64), 256, smem, s>>>(dy_hi, dy_lo, pooled_hi, am, dx, N, C, H, W); clb::count_launch();
+    return CLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ bias gradient
+// db[k] = sum over pixels of dY[pix][k].  Two deterministic stages: kBiasChunks CTAs sum a contiguous pixel range each (thread =
+// channel pair, fixed order), then one pass adds the chunk partials in order.  No atomics: bit-reproducible.
+constexpr int kBiasChunks = 296;
+__global__ void __launch_bounds__(256) bias_partials_kernel(const uint16_t* __restrict__ dy_hi, const uint16_t* __restrict__ dy_lo,
+                                                            float* __restrict__ part, int64_t npix, int K, int64_t pix_per_chunk) {
+    const int K2 = K >> 1;
+    const int tpr = K2 < 256 ? K2 : 256;                            // threads per pixel row (one channel pair each)
+    const int rows = 256 / tpr;                                     // pixel rows in flight
+    const int sub = threadIdx.x / tpr, lc = threadIdx.x % tpr;
+    const int64_t p0 = (int64_t)blockIdx.x * pix_per_chunk, p1 = min(npix, p0 + pix_per_chunk);
+    __shared__ float red[512];
+    for (int c2 = lc; c2 < K2; c2 += tpr) {                         // same trip count for every thread
+        float s0 = 0.f, s1 = 0.f;
+        if (sub < rows)
+            for (int64_t p = p0 + sub; p < p1; p += rows) {
+                const uint32_t h = __ldg(reinterpret_cast<const uint32_t*>(dy_hi + p * K) + c2);
+                const uint32_t l = __ldg(reinterpret_cast<const uint32_t*>(dy_lo + p * K) + c2);
+                s0 += __uint_as_float(h << 16) + __uint_as_float(l << 16);
+                s1 += __uint_as_float(h & 0xFFFF0000u) + __uint_as_float(l & 0xFFFF0000u);
+            }
+        red[2 * threadIdx.x] = s0; red[2 * threadIdx.x + 1] = s1;
+        __syncthreads();
+        if (sub == 0) {
+            for (int r = 1; r < rows; ++r) { s0 += red[2 * (r * tpr + lc)]; s1 += red[2 * (r * tpr + lc) + 1]; }
+            part[(int64_t)blockIdx.x * K + 2 * c2] = s0;
+            part[(int64_t)blockIdx.x * K + 2 * c2 + 1] = s1;
+        }
+        __syncthreads();
+    }
+}
+__global__ void bias_final_kernel(const float* __restrict__ part, float* __restrict__ db, int K, int chunks) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    float s = part[k];
+    for (int c = 1; c < chunks; ++c) s += part[(int64_t)c * K + k];
+    db[k] = s;
+}
+size_t bias_ws_floats(int K) { return (size_t)kBiasChunks * K; }
+int bias_grad(const uint16_t* dy_hi, const uint16_t* dy_lo, float* db, float* part, int64_t npix, int K, cudaStream_t s) {
+    const int64_t per = (npix + kBiasChunks - 1) / kBiasChunks;
+    const int chunks = (int)((npix + per - 1) / per);
+    bias_partials_kernel<<<chunks, 256, 0, s>>>(dy_hi, dy_lo, part, npix, K, per); clb::count_launch();
+    bias_final_kernel<<<(K + 127) / 128, 128, 0, s>>>(part, db, K, chunks); clb::count_launch();
+    return CLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ split-K reduction
+// dw[k][c][tap] = sum_z ws[z][k][tap][c]   (fixed summation order -> bit-reproducible), optionally followed in the same pass
+// by the importance update of the reference's passes over the batch gradient (J-1: "fused into the backward pass"):
+//   imp_mode 1 (EWC, main_EWC.py:151-156):  omega += dw * dw / imp_a
+//   imp_mode 2 (MAS, train_MAS.py:163-177): omega = (omega * imp_a + |dw|) / imp_b
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, float* __restrict__ omega,
+                                                           int K, int C, int splits, int imp_mode, float imp_a, float imp_b) {
+    const int64_t total = (int64_t)K * C * 9, gs = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gs) {
+        const int c = (int)(i % C), t = (int)((i / C) % 9), k = (int)(i / ((int64_t)C * 9));
+        float s = ws[i];
+        for (int z = 1; z < splits; ++z) s += ws[(int64_t)z * total + i];
+        const int64_t o = ((int64_t)k * C + c) * 9 + t;
+        dw[o] = s;
+        if (imp_mode == 1) omega[o] = __fadd_rn(omega[o], __fdiv_rn(__fmul_rn(s, s), imp_a));
+        else if (imp_mode == 2) omega[o] = __fdiv_rn(__fadd_rn(__fmul_rn(omega[o], imp_a), fabsf(s)), imp_b);
+    }
+}
+int wgrad_reduce(const float* ws, float* dw, float* omega, int K, int C, int splits, int imp_mode, float imp_a, float imp_b,
+                 cudaStream_t s) {
+    wgrad_reduce_kernel<<<ew_grid((int64_t)K * C * 9, 256), 256, 0, s>>>(ws, dw, omega, K, C, splits, imp_mode, imp_a, imp_b); clb::count_launch();
+    return CLB_OK;
+}
+
+}  // namespace pl
+}  // namespace clb

@@ -106,6 +106,49 @@ int clb_softmax_loss(const float* logits, int ld, int col_off, int ncols, const 
                      float mean_denominator, float* loss_out, int* correct_out, float* dlogits, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * NHWC bf16 hi/lo "planes" pipeline (a2).  The VGG conv stacks (models/VGGSlim.py:27-40: 3x3 / stride 1 / pad 1 convs,
+ * ReLU, 2x2 max-pools) keep every activation x as two bf16 planes x = hi + lo in NHWC so that both operands of every
+ * conv GEMM are TMA box loads (csrc/clb_planes_conv.cu).  Plane pointers are `void*` to device arrays of uint16 (bf16
+ * bit patterns), `[N][H][W][C]`; weights planes are `[K][tap][C]` (forward) and `[C][8 - tap][K]` (dgrad).
+ * Same replaced call sites as clb_conv2d_* / clb_maxpool_*: model(inputs) / loss.backward() of train_EWC.py:181-187.
+ * ---------------------------------------------------------------------------------------- */
+
+/* 1 when a Conv2d(C -> K, RxS, stride, pad) on an HxW map can run on the planes kernels (3x3/1/1, C % 64 == K % 64 == 0,
+ * power-of-two maps 4 <= W <= 64) */
+int clb_planes_conv_supported(int C, int H, int W, int K, int R, int S, int stride, int pad);
+/* w [K][C][3][3] fp32 -> forward planes wf_{hi,lo} [K][9][C] and (when non-NULL) dgrad planes wt_{hi,lo} [C][9][K] */
+int clb_planes_weights(const float* w, void* wf_hi, void* wf_lo, void* wt_hi, void* wt_lo, int K, int C, void* stream);
+/* y = conv3x3(x, w) + bias, optional fused ReLU; x planes [N][H][W][C], y planes [N][H][W][K]   (nn.Conv2d + nn.ReLU) */
+int clb_planes_conv_fwd(const void* x_hi, const void* x_lo, const void* wf_hi, const void* wf_lo, const float* bias, void* y_hi,
+                        void* y_lo, int N, int H, int W, int C, int K, int relu, void* stream);
+/* dx = conv2d_backward_input(dy, w); mask_hi (may be NULL): hi plane of this conv's (post-ReLU) INPUT activation -- dx is
+ * zeroed where it is <= 0, i.e. the ReLU backward of the layer in front is fused into the epilogue */
+int clb_planes_conv_dgrad(const void* dy_hi, const void* dy_lo, const void* wt_hi, const void* wt_lo, const void* mask_hi, void* dx_hi,
+                          void* dx_lo, int N, int H, int W, int C, int K, void* stream);
+/* dw [K][C][3][3] fp32 = conv2d_backward_weight(x, dy), dbias = sum dy (may be NULL); deterministic split-K.
+ * imp_mode != 0 fuses the importance update of the batch gradient into the split-K reduction (north_star "fused into the
+ * backward pass"):  1: omega += dw*dw / imp_a   (diag_fisher, EWC/main_EWC.py:151-156)
+ *                   2: omega = (omega*imp_a + |dw|) / imp_b   (Objective_After_SGD.step, MAS/train_MAS.py:163-177)
+ * omega: the [K][C][3][3] slot of the flat importance buffer. */
+size_t clb_planes_conv_wgrad_ws(int N, int H, int W, int C, int K);
+int clb_planes_conv_wgrad(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, float* dw, float* dbias, float* ws,
+                          size_t ws_bytes, int N, int H, int W, int C, int K, int imp_mode, float* omega, float imp_a, float imp_b,
+                          void* stream);
+/* MaxPool2d(2, 2) on planes (first maximum wins, like ATen).  Output: planes [N][H/2][W/2][C], or -- y_f32 != NULL -- fp32
+ * [N][C][H/2][W/2] (the classifier's flatten order).  argmax: [N][H/2][W/2][C] window-local index. */
+int clb_planes_pool_fwd(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, float* y_f32, uint8_t* argmax, int N, int H, int W,
+                        int C, void* stream);
+/* same, from an fp32 NCHW input (output of a conv that does not run on the planes kernels, e.g. the C = 3 first layer) */
+int clb_planes_pool_fwd_nchw(const float* x, void* y_hi, void* y_lo, uint8_t* argmax, int N, int C, int H, int W, void* stream);
+/* max-pool backward fused with the ReLU backward of the conv in front: dx[window] = (argmax && pooled > 0) ? dy : 0.
+ * dy / pooled activation either as planes or (dy_f32, pooled_f32 != NULL) as fp32 [N][C][H/2][W/2]; H, W = INPUT size */
+int clb_planes_pool_bwd(const void* dy_hi, const void* dy_lo, const float* dy_f32, const void* pooled_hi, const float* pooled_f32,
+                        const uint8_t* argmax, void* dx_hi, void* dx_lo, int N, int H, int W, int C, void* stream);
+/* same with an fp32 NCHW result [N][C][H][W] (dY of a conv that does not run on the planes kernels) */
+int clb_planes_pool_bwd_nchw(const void* dy_hi, const void* dy_lo, const void* pooled_hi, const uint8_t* argmax, float* dx, int N, int C,
+                             int H, int W, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Optimiser / importance streaming kernels (a4-a11).  One launch over the flat parameter buffer.
  * ---------------------------------------------------------------------------------------- */
 

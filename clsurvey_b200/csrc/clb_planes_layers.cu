@@ -234,32 +234,40 @@ int pool_bwd_to_nchw(const uint16_t* dy_hi, const uint16_t* dy_lo, const uint16_
 // ------------------------------------------------------------------------------------------------ bias gradient
 // db[k] = sum over pixels of dY[pix][k].  Two deterministic stages: kBiasChunks CTAs sum a contiguous pixel range each (thread =
 // channel pair, fixed order), then one pass adds the chunk partials in order.  No atomics: bit-reproducible.
-constexpr int kBiasChunks = 296;
+constexpr int kBiasChunks = 592;
 __global__ void __launch_bounds__(256) bias_partials_kernel(const uint16_t* __restrict__ dy_hi, const uint16_t* __restrict__ dy_lo,
                                                             float* __restrict__ part, int64_t npix, int K, int64_t pix_per_chunk) {
-    const int K2 = K >> 1;
-    const int tpr = K2 < 256 ? K2 : 256;                            // threads per pixel row (one channel pair each)
-    const int rows = 256 / tpr;                                     // pixel rows in flight
-    const int sub = threadIdx.x / tpr, lc = threadIdx.x % tpr;
+    // thread = 8 channels (one 16-byte load per plane) of every `rows`-th pixel of the chunk; K <= 2048
+    const int K8 = K >> 3;
+    const int rows = 256 / K8;                                      // pixel rows in flight (K8 <= 256)
+    const int sub = threadIdx.x / K8, c8 = threadIdx.x - sub * K8;
     const int64_t p0 = (int64_t)blockIdx.x * pix_per_chunk, p1 = min(npix, p0 + pix_per_chunk);
-    __shared__ float red[512];
-    for (int c2 = lc; c2 < K2; c2 += tpr) {                         // same trip count for every thread
-        float s0 = 0.f, s1 = 0.f;
-        if (sub < rows)
-            for (int64_t p = p0 + sub; p < p1; p += rows) {
-                const uint32_t h = __ldg(reinterpret_cast<const uint32_t*>(dy_hi + p * K) + c2);
-                const uint32_t l = __ldg(reinterpret_cast<const uint32_t*>(dy_lo + p * K) + c2);
-                s0 += __uint_as_float(h << 16) + __uint_as_float(l << 16);
-                s1 += __uint_as_float(h & 0xFFFF0000u) + __uint_as_float(l & 0xFFFF0000u);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (sub < rows) {
+        const uint4* hp = reinterpret_cast<const uint4*>(dy_hi) + c8;
+        const uint4* lp = reinterpret_cast<const uint4*>(dy_lo) + c8;
+#pragma unroll 4
+        for (int64_t p = p0 + sub; p < p1; p += rows) {
+            const uint4 h = __ldg(hp + p * K8), l = __ldg(lp + p * K8);
+            const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                acc[2 * j] += __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+                acc[2 * j + 1] += __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
             }
-        red[2 * threadIdx.x] = s0; red[2 * threadIdx.x + 1] = s1;
-        __syncthreads();
-        if (sub == 0) {
-            for (int r = 1; r < rows; ++r) { s0 += red[2 * (r * tpr + lc)]; s1 += red[2 * (r * tpr + lc) + 1]; }
-            part[(int64_t)blockIdx.x * K + 2 * c2] = s0;
-            part[(int64_t)blockIdx.x * K + 2 * c2 + 1] = s1;
         }
-        __syncthreads();
+    }
+    __shared__ float red[256 * 9];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x * 9 + j] = acc[j];
+    __syncthreads();
+    for (int i = threadIdx.x; i < K; i += 256) {                    // fixed-order sum over the rows
+        const int cc8 = i >> 3, j = i & 7;
+        float s = 0.f;
+        for (int r = 0; r < rows; ++r) s += red[(r * K8 + cc8) * 9 + j];
+        part[(int64_t)blockIdx.x * K + i] = s;
     }
 }
 __global__ void bias_final_kernel(const float* __restrict__ part, float* __restrict__ db, int K, int chunks) {
@@ -285,20 +293,38 @@ int bias_grad(const uint16_t* dy_hi, const uint16_t* dy_lo, float* db, float* pa
 //   imp_mode 2 (MAS, train_MAS.py:163-177): omega = (omega * imp_a + |dw|) / imp_b
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, float* __restrict__ omega,
                                                            int K, int C, int splits, int imp_mode, float imp_a, float imp_b) {
-    const int64_t total = (int64_t)K * C * 9, gs = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gs) {
-        const int c = (int)(i % C), t = (int)((i / C) % 9), k = (int)(i / ((int64_t)C * 9));
-        float s = ws[i];
-        for (int z = 1; z < splits; ++z) s += ws[(int64_t)z * total + i];
-        const int64_t o = ((int64_t)k * C + c) * 9 + t;
-        dw[o] = s;
-        if (imp_mode == 1) omega[o] = __fadd_rn(omega[o], __fdiv_rn(__fmul_rn(s, s), imp_a));
-        else if (imp_mode == 2) omega[o] = __fdiv_rn(__fadd_rn(__fmul_rn(omega[o], imp_a), fabsf(s)), imp_b);
+    // warp = 32 consecutive channels of one filter k: reads are coalesced along c (ws is [z][k][tap][c]), the 288 results are
+    // transposed through shared memory and written as one contiguous run of dw[k][c0..c0+31][9]
+    __shared__ float buf[8][288];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t total = (int64_t)K * C * 9;
+    const int cg = C >> 5;                                           // C % 64 == 0
+    const int64_t n_groups = (int64_t)K * cg;
+    for (int64_t g = (int64_t)blockIdx.x * 8 + warp; g < n_groups; g += (int64_t)gridDim.x * 8) {
+        const int k = (int)(g / cg), c0 = (int)(g - (int64_t)k * cg) * 32;
+        const float* src = ws + ((int64_t)k * 9) * C + c0 + lane;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            float s = src[(int64_t)t * C];
+            for (int z = 1; z < splits; ++z) s += src[(int64_t)z * total + (int64_t)t * C];
+            buf[warp][lane * 9 + t] = s;
+        }
+        __syncwarp();
+        const int64_t o0 = ((int64_t)k * C + c0) * 9;
+#pragma unroll
+        for (int it = 0; it < 9; ++it) {
+            const float s = buf[warp][it * 32 + lane];
+            const int64_t o = o0 + it * 32 + lane;
+            dw[o] = s;
+            if (imp_mode == 1) omega[o] = __fadd_rn(omega[o], __fdiv_rn(__fmul_rn(s, s), imp_a));
+            else if (imp_mode == 2) omega[o] = __fdiv_rn(__fadd_rn(__fmul_rn(omega[o], imp_a), fabsf(s)), imp_b);
+        }
+        __syncwarp();
     }
 }
 int wgrad_reduce(const float* ws, float* dw, float* omega, int K, int C, int splits, int imp_mode, float imp_a, float imp_b,
                  cudaStream_t s) {
-    wgrad_reduce_kernel<<<ew_grid((int64_t)K * C * 9, 256), 256, 0, s>>>(ws, dw, omega, K, C, splits, imp_mode, imp_a, imp_b); clb::count_launch();
+    wgrad_reduce_kernel<<<ew_grid((int64_t)K * C, 32), 256, 0, s>>>(ws, dw, omega, K, C, splits, imp_mode, imp_a, imp_b); clb::count_launch();
     return CLB_OK;
 }
 

@@ -15,6 +15,7 @@ Layout in HBM:
       uint8 arg-max per max-pool, two ping-pong gradient buffers.
 """
 import ctypes
+import os
 import weakref
 
 import torch
@@ -207,14 +208,19 @@ class Engine:
         self.ops = ops
         self.n_outputs = feat
         B = self.max_batch
+        self._plan_planes()
         max_act = 1
         for op in ops:
             n = 1
             for d in op["out_shape"]:
                 n *= d
             op["out_numel"] = n
-            op["out"] = torch.empty(B * n, dtype=torch.float32, device=self.device)
-            max_act = max(max_act, n)
+            lay_out = op.get("lay_out", "nchw")
+            if lay_out == "nchw":
+                op["out"] = torch.empty(B * n, dtype=torch.float32, device=self.device)
+                max_act = max(max_act, n)
+            elif not op.get("transient"):                 # bf16 hi / lo planes, NHWC (csrc/clb_planes_conv.cu)
+                op["out_pl"] = torch.empty(2, B * n, dtype=torch.int16, device=self.device)
             if op["kind"] == "maxpool":
                 op["argmax"] = torch.empty(B * n, dtype=torch.uint8, device=self.device)
         in_numel = self.input_shape[0] * self.input_shape[1] * self.input_shape[2]
@@ -222,7 +228,19 @@ class Engine:
         self.dbuf = [torch.empty(B * max_act, dtype=torch.float32, device=self.device) for _ in range(2)]
         self.dlogits = torch.empty(B * self.n_outputs, dtype=torch.float32, device=self.device)
         ws_bytes, wt_elems = 16, 4
+        pl_max = max([op["out_numel"] for op in ops if op.get("lay_out") == "planes"] +
+                     [op["C"] * op["H"] * op["W"] for op in ops if op["kind"] == "conv" and op.get("planes")] + [0])
+        self.pl_scratch = self.dpl = None
+        if pl_max:
+            self.pl_scratch = torch.empty(2, B * pl_max, dtype=torch.int16, device=self.device)      # pre-pool conv outputs
+            self.dpl = [torch.empty(2, B * pl_max, dtype=torch.int16, device=self.device) for _ in range(2)]
         for op in ops:
+            if op["kind"] == "conv" and op.get("planes"):
+                K, C = op["K"], op["C"]
+                op["wf"] = torch.empty(2, K * 9 * C, dtype=torch.int16, device=self.device)   # [K][tap][C] hi / lo
+                op["wt"] = torch.empty(2, K * 9 * C, dtype=torch.int16, device=self.device)   # [C][8 - tap][K] hi / lo
+                ws_bytes = max(ws_bytes, _capi.lib().clb_planes_conv_wgrad_ws(B, op["H"], op["W"], C, K))
+                continue
             if op["kind"] == "conv":
                 ws_bytes = max(ws_bytes, _capi.lib().clb_conv2d_wgrad_ws(B, op["C"], op["H"], op["W"], op["K"], op["R"],
                                                                           op["S"], op["stride"], op["pad"]))
@@ -237,6 +255,52 @@ class Engine:
         self.correct_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.n_launch = 0
 
+    def _plan_planes(self):
+        """Mark the convs that run on the planes kernels (3x3/1/1 + ReLU, C % 64 == K % 64 == 0, power-of-two maps) and the
+        layout ('nchw' fp32 | 'planes' bf16 hi/lo NHWC) of every features op's output.  A planes conv reads planes: from a
+        planes conv directly or through a 2x2/2 max-pool (which converts from an fp32 NCHW producer if need be); it hands its
+        output to a planes conv or to a 2x2/2 max-pool (which converts back to fp32 NCHW for any other consumer)."""
+        ops = self.ops
+        nfeat = next((i for i, op in enumerate(ops) if op["kind"] in ("avgpool", "linear", "dropout")), len(ops))
+        lib = _capi.lib()
+        self._plan_mode = lib.clb_get_matmul_mode()
+        if os.environ.get("CLB_PLANES", "1") == "0" or self._plan_mode != 3:
+            return
+
+        def pool22(op):
+            return op["kind"] == "maxpool" and op["k"] == 2 and op["stride"] == 2 and op["H"] % 2 == 0 and op["W"] % 2 == 0
+
+        for i in range(nfeat):
+            op = ops[i]
+            op["planes"] = bool(op["kind"] == "conv" and op["relu"] and op["b"] is not None and lib.clb_planes_conv_supported(
+                op["C"], op["H"], op["W"], op["K"], op["R"], op["S"], op["stride"], op["pad"]))
+        changed = True
+        while changed:
+            changed = False
+            for i in range(nfeat):
+                op = ops[i]
+                if not op.get("planes"):
+                    continue
+                prev = ops[i - 1] if i > 0 else None
+                pprev = ops[i - 2] if i > 1 else None
+                in_ok = prev is not None and (prev.get("planes") or (
+                    pool22(prev) and pprev is not None and pprev["kind"] == "conv" and pprev["relu"] and
+                    (pprev.get("planes") or (pprev["K"] % 64 == 0 and prev["W"] <= 128))))
+                nxt = ops[i + 1] if i + 1 < nfeat else None
+                out_ok = nxt is not None and (nxt.get("planes") or pool22(nxt))
+                if not (in_ok and out_ok):
+                    op["planes"] = False
+                    changed = True
+        for i in range(nfeat):
+            op = ops[i]
+            nxt = ops[i + 1] if i + 1 < nfeat else None
+            if op["kind"] == "conv" and op.get("planes"):
+                op["lay_out"] = "planes"
+                op["transient"] = nxt is not None and nxt["kind"] == "maxpool"     # only the pool reads it
+            elif op["kind"] == "maxpool":
+                op["lay_in"] = "planes" if (i > 0 and ops[i - 1].get("planes")) else "nchw"
+                op["lay_out"] = "planes" if (nxt is not None and nxt.get("planes")) else "nchw"
+
     # ------------------------------------------------------------------ forward
     def forward(self, x, train=False, masks=None):
         """x: [n, C, H, W] fp32 CUDA contiguous.  Returns logits [n, n_outputs] (a view of an internal buffer).
@@ -246,6 +310,9 @@ class Engine:
         x = x.contiguous()
         assert tuple(x.shape[1:]) == self.input_shape, (x.shape, self.input_shape)
         s = _stream()
+        if _capi.lib().clb_get_matmul_mode() != self._plan_mode:     # the planes / legacy split follows the matmul mode
+            self._graphs = {}
+            self._compile()
         cur = x
         self._n = n
         self._train = train
@@ -253,7 +320,32 @@ class Engine:
         for op in self.ops:
             op["inp"] = cur
             k = op["kind"]
-            if k == "conv":
+            if k == "conv" and op.get("planes"):
+                # cur = (hi, lo) planes [n][H][W][C]; weights re-ordered into bf16 planes for fwd and dgrad in one launch
+                call("clb_planes_weights", _ptr(self.view(self.theta, op["w"])), _ptr(op["wf"][0]), _ptr(op["wf"][1]),
+                     _ptr(op["wt"][0]), _ptr(op["wt"][1]), op["K"], op["C"], s)
+                out = self.pl_scratch if op["transient"] else op["out_pl"]
+                self._timed(call, "clb_planes_conv_fwd", _ptr(cur[0]), _ptr(cur[1]), _ptr(op["wf"][0]), _ptr(op["wf"][1]),
+                            _ptr(self.view(self.theta, op["b"])), _ptr(out[0]), _ptr(out[1]), n, op["H"], op["W"], op["C"],
+                            op["K"], 1, s)
+                cur = out
+                self.n_launch += 1
+            elif k == "maxpool" and (op.get("lay_in") == "planes" or op.get("lay_out") == "planes"):
+                if op["lay_in"] == "nchw":                            # fp32 NCHW (legacy conv + ReLU) -> planes
+                    out = op["out_pl"]
+                    call("clb_planes_pool_fwd_nchw", _ptr(cur), _ptr(out[0]), _ptr(out[1]), _ptr(op["argmax"]), n, op["C"],
+                         op["H"], op["W"], s)
+                    cur = out
+                elif op["lay_out"] == "planes":
+                    out = op["out_pl"]
+                    call("clb_planes_pool_fwd", _ptr(cur[0]), _ptr(cur[1]), _ptr(out[0]), _ptr(out[1]), 0, _ptr(op["argmax"]),
+                         n, op["H"], op["W"], op["C"], s)
+                    cur = out
+                else:                                                 # planes -> fp32 NCHW (classifier / legacy consumer)
+                    call("clb_planes_pool_fwd", _ptr(cur[0]), _ptr(cur[1]), 0, 0, _ptr(op["out"]), _ptr(op["argmax"]), n,
+                         op["H"], op["W"], op["C"], s)
+                    cur = op["out"]
+            elif k == "conv":
                 self._timed(call, "clb_conv2d_fwd", _ptr(cur), _ptr(self.view(self.theta, op["w"])),
                      _ptr(self.view(self.theta, op["b"])) if op["b"] is not None else 0, _ptr(op["out"]),
                      _ptr(self.wt_ws), n, op["C"], op["H"], op["W"], op["K"], op["R"], op["S"], op["stride"], op["pad"],
@@ -344,7 +436,7 @@ class Engine:
             if self._grad_alt is None:
                 self._grad_alt = torch.zeros_like(self.grad)
             gdst = self._grad_alt
-        d, other = self.dlogits, 0
+        d, other, pl_other = self.dlogits, 0, 0
         first_param_op = next(i for i, op in enumerate(self.ops) if op["kind"] in ("conv", "linear"))
         relu_done = set()
         for i in range(len(self.ops) - 1, -1, -1):
@@ -374,6 +466,39 @@ class Engine:
                 nxt = self.dbuf[other]
                 call("clb_adaptive_avgpool_bwd", _ptr(d), _ptr(nxt), n, op["C"], op["H"], op["W"], op["OH"], op["OW"], s)
                 d, other = nxt, other ^ 1
+            elif k == "maxpool" and (op.get("lay_in") == "planes" or op.get("lay_out") == "planes"):
+                # max-pool backward fused with the ReLU backward of the conv in front (pooled > 0 <=> selected input > 0)
+                if op["lay_in"] == "nchw":                            # d planes -> fp32 NCHW dY of a legacy conv
+                    nxt = self.dbuf[other]
+                    call("clb_planes_pool_bwd_nchw", _ptr(d[0]), _ptr(d[1]), _ptr(op["out_pl"][0]), _ptr(op["argmax"]),
+                         _ptr(nxt), n, op["C"], op["H"], op["W"], s)
+                    d, other = nxt, other ^ 1
+                else:
+                    nxt = self.dpl[pl_other]
+                    if op["lay_out"] == "nchw":                       # fp32 NCHW d (classifier side) -> planes
+                        call("clb_planes_pool_bwd", 0, 0, _ptr(d), 0, _ptr(op["out"]), _ptr(op["argmax"]), _ptr(nxt[0]),
+                             _ptr(nxt[1]), n, op["H"], op["W"], op["C"], s)
+                    else:
+                        call("clb_planes_pool_bwd", _ptr(d[0]), _ptr(d[1]), 0, _ptr(op["out_pl"][0]), 0, _ptr(op["argmax"]),
+                             _ptr(nxt[0]), _ptr(nxt[1]), n, op["H"], op["W"], op["C"], s)
+                    d, pl_other = nxt, pl_other ^ 1
+                relu_done.add(i - 1)
+                self.n_launch += 1
+            elif k == "conv" and op.get("planes"):
+                x_pl = op["inp"]                                      # planes of this conv's (post-ReLU) input
+                self._timed(call, "clb_planes_conv_wgrad", _ptr(x_pl[0]), _ptr(x_pl[1]), _ptr(d[0]), _ptr(d[1]),
+                            _ptr(self.view(gdst, op["w"])), _ptr(self.view(gdst, op["b"])), _ptr(self.ws), self.ws.numel() * 4,
+                            n, op["H"], op["W"], op["C"], op["K"], 0, 0, 0.0, 0.0, s)
+                prev = self.ops[i - 1]
+                nxt = self.dpl[pl_other]
+                mask = 0
+                if prev.get("planes"):                                # ReLU backward of the conv in front, fused
+                    mask = _ptr(x_pl[0])
+                    relu_done.add(i - 1)
+                self._timed(call, "clb_planes_conv_dgrad", _ptr(d[0]), _ptr(d[1]), _ptr(op["wt"][0]), _ptr(op["wt"][1]), mask,
+                            _ptr(nxt[0]), _ptr(nxt[1]), n, op["H"], op["W"], op["C"], op["K"], s)
+                d, pl_other = nxt, pl_other ^ 1
+                self.n_launch += 5
             elif k == "maxpool":
                 prev = self.ops[i - 1] if i > 0 else None
                 fuse = prev is not None and prev["kind"] == "conv" and prev["relu"]

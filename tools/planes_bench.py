@@ -10,6 +10,7 @@ _capi.lib()
 dev = "cuda"
 S = lambda: torch.cuda.current_stream().cuda_stream
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+ONCE = "once" in sys.argv            # one call per kernel (for ncu)
 LAYERS = [(32, 64, 128), (16, 128, 256), (16, 256, 256), (8, 256, 512), (8, 512, 512), (4, 512, 512), (4, 512, 512)]
 
 
@@ -21,6 +22,10 @@ def planes(*shape):
 
 
 def timeit(fn, reps=20):
+    if ONCE:
+        fn()
+        torch.cuda.synchronize()
+        return 1.0
     for _ in range(3):
         fn()
     torch.cuda.synchronize()

@@ -4,6 +4,8 @@
 namespace clb {
 namespace pl {
 int weights_to_planes(const float* w, uint16_t* wf_hi, uint16_t* wf_lo, uint16_t* wt_hi, uint16_t* wt_lo, int K, int C, cudaStream_t s);
+int weights_to_planes_batch(int n, const float* const* w, void* const* wf_hi, void* const* wf_lo, void* const* wt_hi, void* const* wt_lo,
+                            const int* K, const int* C, cudaStream_t s);
 int pool_fwd(const uint16_t* x_hi, const uint16_t* x_lo, uint16_t* y_hi, uint16_t* y_lo, float* y_f32, uint8_t* am, int N, int H, int W,
              int C, cudaStream_t s);
 int pool_fwd_from_nchw(const float* x, uint16_t* y_hi, uint16_t* y_lo, uint8_t* am, int N, int C, int H, int W, cudaStream_t s);
@@ -29,6 +31,16 @@ int clb_planes_conv_supported(int C, int H, int W, int K, int R, int S, int stri
 int clb_planes_weights(const float* w, void* wf_hi, void* wf_lo, void* wt_hi, void* wt_lo, int K, int C, void* stream) {
     CLB_CHECK_ARG(w && wf_hi && wf_lo && K > 0 && C > 0 && ((wt_hi == nullptr) == (wt_lo == nullptr)));
     int rc = pl::weights_to_planes(w, (u16*)wf_hi, (u16*)wf_lo, (u16*)wt_hi, (u16*)wt_lo, K, C, as_stream(stream));
+    if (rc) return rc;
+    CLB_CHECK_LAUNCH();
+    return CLB_OK;
+}
+
+int clb_planes_weights_batch(int n, const float* const* w, void* const* wf_hi, void* const* wf_lo, void* const* wt_hi, void* const* wt_lo,
+                              const int* K, const int* C, void* stream) {
+    CLB_CHECK_ARG(n > 0 && n <= 24 && w && wf_hi && wf_lo && wt_hi && wt_lo && K && C);
+    for (int i = 0; i < n; ++i) CLB_CHECK_ARG(w[i] && wf_hi[i] && wf_lo[i] && wt_hi[i] && wt_lo[i] && K[i] > 0 && C[i] > 0);
+    int rc = pl::weights_to_planes_batch(n, w, wf_hi, wf_lo, wt_hi, wt_lo, K, C, as_stream(stream));
     if (rc) return rc;
     CLB_CHECK_LAUNCH();
     return CLB_OK;

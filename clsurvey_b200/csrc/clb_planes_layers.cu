@@ -48,6 +48,54 @@ int weights_to_planes(const float* w, uint16_t* wf_hi, uint16_t* wf_lo, uint16_t
     return CLB_OK;
 }
 
+// all planes convs of a model in ONE launch (blockIdx.y = 2 * layer + layout): a VGG-11 step otherwise pays seven ~12 us
+// latency-bound launches for 37 MB of weights
+struct WeightBatch {
+    static constexpr int kMax = 24;
+    int n;
+    const float* w[kMax];
+    uint16_t *wf_hi[kMax], *wf_lo[kMax], *wt_hi[kMax], *wt_lo[kMax];
+    int K[kMax], C[kMax];
+};
+__global__ void __launch_bounds__(256) weights_to_planes_batch_kernel(const __grid_constant__ WeightBatch b) {
+    const int layer = blockIdx.y >> 1;
+    const bool dgrad = blockIdx.y & 1;
+    const int K = b.K[layer], C = b.C[layer];
+    const float* __restrict__ w = b.w[layer];
+    uint16_t* __restrict__ o_hi = dgrad ? b.wt_hi[layer] : b.wf_hi[layer];
+    uint16_t* __restrict__ o_lo = dgrad ? b.wt_lo[layer] : b.wf_lo[layer];
+    const int64_t total = (int64_t)K * C, gs = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gs) {
+        int k, c;
+        if (!dgrad) { k = (int)(i / C); c = (int)(i - (int64_t)k * C); }
+        else { c = (int)(i / K); k = (int)(i - (int64_t)c * K); }
+        const float* src = w + ((int64_t)k * C + c) * 9;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            uint32_t hi, lo;
+            split1(__ldg(src + t), hi, lo);
+            const int64_t o = dgrad ? ((int64_t)c * 9 + (8 - t)) * K + k : ((int64_t)k * 9 + t) * C + c;
+            o_hi[o] = (uint16_t)hi; o_lo[o] = (uint16_t)lo;
+        }
+    }
+}
+int weights_to_planes_batch(int n, const float* const* w, void* const* wf_hi, void* const* wf_lo, void* const* wt_hi, void* const* wt_lo,
+                            const int* K, const int* C, cudaStream_t s) {
+    WeightBatch b;
+    b.n = n;
+    int64_t mx = 1;
+    for (int i = 0; i < n; ++i) {
+        b.w[i] = w[i]; b.wf_hi[i] = (uint16_t*)wf_hi[i]; b.wf_lo[i] = (uint16_t*)wf_lo[i];
+        b.wt_hi[i] = (uint16_t*)wt_hi[i]; b.wt_lo[i] = (uint16_t*)wt_lo[i];
+        b.K[i] = K[i]; b.C[i] = C[i];
+        if ((int64_t)K[i] * C[i] > mx) mx = (int64_t)K[i] * C[i];
+    }
+    int gx = (int)((mx + 255) / 256);
+    if (gx > 256) gx = 256;
+    weights_to_planes_batch_kernel<<<dim3(gx, 2 * n), 256, 0, s>>>(b); clb::count_launch();
+    return CLB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ max-pool 2x2 / 2
 // Window scanned row-major with strict '>' so the FIRST maximum wins (ATen semantics, like clb_maxpool_fwd).
 struct U8x8 { uint32_t a, b; };
@@ -270,19 +318,21 @@ __global__ void __launch_bounds__(256) bias_partials_kernel(const uint16_t* __re
         part[(int64_t)blockIdx.x * K + i] = s;
     }
 }
-__global__ void bias_final_kernel(const float* __restrict__ part, float* __restrict__ db, int K, int chunks) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per channel: lane l adds chunks l, l + 32, ... in order, then a fixed xor-shuffle tree (deterministic)
+__global__ void __launch_bounds__(256) bias_final_kernel(const float* __restrict__ part, float* __restrict__ db, int K, int chunks) {
+    const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (k >= K) return;
-    float s = part[k];
-    for (int c = 1; c < chunks; ++c) s += part[(int64_t)c * K + k];
-    db[k] = s;
+    float s = 0.f;
+    for (int c = lane; c < chunks; c += 32) s += part[(int64_t)c * K + k];
+    s = warp_sum(s);
+    if (lane == 0) db[k] = s;
 }
 size_t bias_ws_floats(int K) { return (size_t)kBiasChunks * K; }
 int bias_grad(const uint16_t* dy_hi, const uint16_t* dy_lo, float* db, float* part, int64_t npix, int K, cudaStream_t s) {
     const int64_t per = (npix + kBiasChunks - 1) / kBiasChunks;
     const int chunks = (int)((npix + per - 1) / per);
     bias_partials_kernel<<<chunks, 256, 0, s>>>(dy_hi, dy_lo, part, npix, K, per); clb::count_launch();
-    bias_final_kernel<<<(K + 127) / 128, 128, 0, s>>>(part, db, K, chunks); clb::count_launch();
+    bias_final_kernel<<<(K + 7) / 8, 256, 0, s>>>(part, db, K, chunks); clb::count_launch();
     return CLB_OK;
 }
 

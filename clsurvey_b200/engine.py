@@ -216,7 +216,9 @@ class Engine:
                 n *= d
             op["out_numel"] = n
             lay_out = op.get("lay_out", "nchw")
-            if lay_out == "nchw":
+            if op.get("fused_first"):
+                pass                                              # its fp32 output (210 MB for VGG-11 / batch 200) never exists
+            elif lay_out == "nchw":
                 op["out"] = torch.empty(B * n, dtype=torch.float32, device=self.device)
                 max_act = max(max_act, n)
             elif not op.get("transient"):                 # bf16 hi / lo planes, NHWC (csrc/clb_planes_conv.cu)
@@ -246,9 +248,20 @@ class Engine:
                                                                           op["S"], op["stride"], op["pad"]))
                 # re-ordered weights for the tensor-core path: hi + lo plane, each max(K*C*R*S, 32*K, 32*C) floats
                 wt_elems = max(wt_elems, 2 * (max(op["K"] * op["C"] * op["R"] * op["S"], op["K"] * 32, op["C"] * 32) + 4))
+        if any(op.get("fused_first") for op in ops):
+            ws_bytes = max(ws_bytes, _capi.lib().clb_planes_conv1_ws())
         for op in ops:
             if op["kind"] == "linear":
                 ws_bytes = max(ws_bytes, _capi.lib().clb_linear_ws(B, op["inf"], op["outf"]))
+        self._wbatch = None
+        pconvs = [op for op in ops if op["kind"] == "conv" and op.get("planes")]
+        if pconvs:
+            n = len(pconvs)
+            P, I = ctypes.c_void_p * n, ctypes.c_int * n
+            self._wbatch = (n, P(*[_ptr(self.view(self.theta, op["w"])) for op in pconvs]),
+                            P(*[_ptr(op["wf"][0]) for op in pconvs]), P(*[_ptr(op["wf"][1]) for op in pconvs]),
+                            P(*[_ptr(op["wt"][0]) for op in pconvs]), P(*[_ptr(op["wt"][1]) for op in pconvs]),
+                            I(*[op["K"] for op in pconvs]), I(*[op["C"] for op in pconvs]))
         self.ws = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=self.device)
         self.wt_ws = torch.empty(wt_elems, dtype=torch.float32, device=self.device)
         self.loss_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
@@ -300,6 +313,13 @@ class Engine:
             elif op["kind"] == "maxpool":
                 op["lay_in"] = "planes" if (i > 0 and ops[i - 1].get("planes")) else "nchw"
                 op["lay_out"] = "planes" if (nxt is not None and nxt.get("planes")) else "nchw"
+                prev = ops[i - 1] if i > 0 else None
+                # first layer (C = 3 -> 64) + ReLU + this pool as ONE kernel each way (csrc/clb_planes_first.cu)
+                if (i == 1 and op["lay_in"] == "nchw" and op["lay_out"] == "planes" and prev["kind"] == "conv" and prev["relu"]
+                        and prev["b"] is not None and os.environ.get("CLB_PLANES_FIRST", "1") != "0"
+                        and lib.clb_planes_conv1_supported(prev["C"], prev["H"], prev["W"], prev["K"], prev["R"], prev["S"],
+                                                           prev["stride"], prev["pad"])):
+                    prev["fused_first"] = op["fused_prev"] = True
 
     # ------------------------------------------------------------------ forward
     def forward(self, x, train=False, masks=None):
@@ -317,13 +337,23 @@ class Engine:
         self._n = n
         self._train = train
         self._masks = {}
+        if self._wbatch is not None:      # weights of all planes convs -> bf16 hi/lo planes (fwd + dgrad layouts), one launch
+            call("clb_planes_weights_batch", *self._wbatch, s)
+            self.n_launch += 1
         for op in self.ops:
             op["inp"] = cur
             k = op["kind"]
-            if k == "conv" and op.get("planes"):
-                # cur = (hi, lo) planes [n][H][W][C]; weights re-ordered into bf16 planes for fwd and dgrad in one launch
-                call("clb_planes_weights", _ptr(self.view(self.theta, op["w"])), _ptr(op["wf"][0]), _ptr(op["wf"][1]),
-                     _ptr(op["wt"][0]), _ptr(op["wt"][1]), op["K"], op["C"], s)
+            if k == "conv" and op.get("fused_first"):
+                pool = self.ops[1]
+                out = pool["out_pl"]
+                self._timed(call, "clb_planes_conv1_pool_fwd", _ptr(cur), _ptr(self.view(self.theta, op["w"])),
+                            _ptr(self.view(self.theta, op["b"])), _ptr(out[0]), _ptr(out[1]), _ptr(pool["argmax"]), n, op["C"],
+                            op["H"], op["W"], op["K"], s)
+                cur = out
+            elif k == "maxpool" and op.get("fused_prev"):
+                continue                                              # done by the conv kernel in front
+            elif k == "conv" and op.get("planes"):
+                # cur = (hi, lo) planes [n][H][W][C]
                 out = self.pl_scratch if op["transient"] else op["out_pl"]
                 self._timed(call, "clb_planes_conv_fwd", _ptr(cur[0]), _ptr(cur[1]), _ptr(op["wf"][0]), _ptr(op["wf"][1]),
                             _ptr(self.view(self.theta, op["b"])), _ptr(out[0]), _ptr(out[1]), n, op["H"], op["W"], op["C"],
@@ -466,6 +496,14 @@ class Engine:
                 nxt = self.dbuf[other]
                 call("clb_adaptive_avgpool_bwd", _ptr(d), _ptr(nxt), n, op["C"], op["H"], op["W"], op["OH"], op["OW"], s)
                 d, other = nxt, other ^ 1
+            elif k == "maxpool" and op.get("fused_prev"):
+                continue                                              # d stays the planes gradient of the pooled output
+            elif k == "conv" and op.get("fused_first"):
+                pool = self.ops[1]
+                self._timed(call, "clb_planes_conv1_pool_bwd", _ptr(op["inp"]), _ptr(d[0]), _ptr(d[1]), _ptr(pool["out_pl"][0]),
+                            _ptr(pool["argmax"]), _ptr(self.view(gdst, op["w"])), _ptr(self.view(gdst, op["b"])), _ptr(self.ws),
+                            self.ws.numel() * 4, n, op["C"], op["H"], op["W"], op["K"], s)
+                self.n_launch += 2
             elif k == "maxpool" and (op.get("lay_in") == "planes" or op.get("lay_out") == "planes"):
                 # max-pool backward fused with the ReLU backward of the conv in front (pooled > 0 <=> selected input > 0)
                 if op["lay_in"] == "nchw":                            # d planes -> fp32 NCHW dY of a legacy conv

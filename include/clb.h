@@ -118,6 +118,9 @@ int clb_softmax_loss(const float* logits, int ld, int col_off, int ncols, const 
 int clb_planes_conv_supported(int C, int H, int W, int K, int R, int S, int stride, int pad);
 /* w [K][C][3][3] fp32 -> forward planes wf_{hi,lo} [K][9][C] and (when non-NULL) dgrad planes wt_{hi,lo} [C][9][K] */
 int clb_planes_weights(const float* w, void* wf_hi, void* wf_lo, void* wt_hi, void* wt_lo, int K, int C, void* stream);
+/* the same for n layers in ONE launch; every argument is a HOST array of n entries (device pointers / sizes), n <= 24 */
+int clb_planes_weights_batch(int n, const float* const* w, void* const* wf_hi, void* const* wf_lo, void* const* wt_hi, void* const* wt_lo,
+                              const int* K, const int* C, void* stream);
 /* y = conv3x3(x, w) + bias, optional fused ReLU; x planes [N][H][W][C], y planes [N][H][W][K]   (nn.Conv2d + nn.ReLU) */
 int clb_planes_conv_fwd(const void* x_hi, const void* x_lo, const void* wf_hi, const void* wf_lo, const float* bias, void* y_hi,
                         void* y_lo, int N, int H, int W, int C, int K, int relu, void* stream);
@@ -134,6 +137,16 @@ size_t clb_planes_conv_wgrad_ws(int N, int H, int W, int C, int K);
 int clb_planes_conv_wgrad(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, float* dw, float* dbias, float* ws,
                           size_t ws_bytes, int N, int H, int W, int C, int K, int imp_mode, float* omega, float imp_a, float imp_b,
                           void* stream);
+/* First layer of the VGG stacks fused with its ReLU and 2x2 max-pool (features[0..2] of VGGSlim.py:27-40: Conv2d(3, 64, 3,
+ * padding=1), ReLU, MaxPool2d(2, 2)): x fp32 NCHW [N][3][H][W] -> planes [N][H/2][W/2][64] + argmax, exact fp32 FFMA.
+ * The backward call fuses max-pool backward, ReLU backward and the weight / bias gradient (dp = gradient w.r.t. the pooled
+ * output, pooled_hi = hi plane of the pooled output).  ws_bytes >= clb_planes_conv1_ws(). */
+int clb_planes_conv1_supported(int C, int H, int W, int K, int R, int S, int stride, int pad);
+int clb_planes_conv1_pool_fwd(const float* x, const float* w, const float* bias, void* y_hi, void* y_lo, uint8_t* argmax, int N, int C,
+                              int H, int W, int K, void* stream);
+size_t clb_planes_conv1_ws(void);
+int clb_planes_conv1_pool_bwd(const float* x, const void* dp_hi, const void* dp_lo, const void* pooled_hi, const uint8_t* argmax, float* dw,
+                              float* dbias, float* ws, size_t ws_bytes, int N, int C, int H, int W, int K, void* stream);
 /* MaxPool2d(2, 2) on planes (first maximum wins, like ATen).  Output: planes [N][H/2][W/2][C], or -- y_f32 != NULL -- fp32
  * [N][C][H/2][W/2] (the classifier's flatten order).  argmax: [N][H/2][W/2][C] window-local index. */
 int clb_planes_pool_fwd(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, float* y_f32, uint8_t* argmax, int N, int H, int W,

@@ -158,12 +158,51 @@ def check_pools():
     report("pool bwd planes -> fp32 NCHW", rel(dxf.cpu(), ref_dx), 0)
 
 
+def check_first():
+    g = torch.Generator().manual_seed(11)
+    for N, H in ((3, 16), (5, 64)):
+        W, K = H, 64
+        x = torch.randn(N, 3, H, W, generator=g)
+        w = torch.randn(K, 3, 3, 3, generator=g) * 0.2
+        b = torch.randn(K, generator=g) * 0.1
+        xd, wd, bd = x.to(dev), w.to(dev), b.to(dev)
+        y = empty_planes(N, H // 2, W // 2, K)
+        am = torch.zeros(N, H // 2, W // 2, K, dtype=torch.uint8, device=dev)
+        call("clb_planes_conv1_pool_fwd", xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), y[0].data_ptr(), y[1].data_ptr(), am.data_ptr(),
+             N, 3, H, W, K, S())
+        torch.cuda.synchronize()
+        xr = x.double().requires_grad_(False)
+        wr = w.double().requires_grad_(True)
+        br = b.double().requires_grad_(True)
+        act = torch.relu(F.conv2d(xr, wr, br, padding=1))
+        pooled, idx = F.max_pool2d(act, 2, 2, return_indices=True)
+        got = from_planes(*y).permute(0, 3, 1, 2)
+        report("conv1+relu+pool fwd N%d %dx%d" % (N, H, W), rel(got, pooled.detach()), 2e-5)
+        # arg-max agreement (window-local index) wherever the pooled value is > 0 and not a near-tie
+        hh, ww = idx // W, idx % W
+        loc = ((hh % 2) * 2 + (ww % 2)).permute(0, 2, 3, 1)
+        agree = ((am.cpu().long() == loc) | (pooled.permute(0, 2, 3, 1) <= 0)).float().mean().item()
+        report("conv1+relu+pool argmax agreement (1 - frac)", 1.0 - agree, 1e-3)
+        dp = quant(torch.randn(N, K, H // 2, W // 2, generator=g))
+        pooled.backward(dp.double())
+        dpp = to_planes(dp.permute(0, 2, 3, 1).contiguous())
+        ws_bytes = _capi.lib().clb_planes_conv1_ws()
+        ws = torch.zeros(ws_bytes // 4 + 4, device=dev)
+        dw = torch.zeros(K, 3, 3, 3, device=dev)
+        db = torch.zeros(K, device=dev)
+        call("clb_planes_conv1_pool_bwd", xd.data_ptr(), dpp[0].data_ptr(), dpp[1].data_ptr(), y[0].data_ptr(), am.data_ptr(), dw.data_ptr(),
+             db.data_ptr(), ws.data_ptr(), ws_bytes, N, 3, H, W, K, S())
+        torch.cuda.synchronize()
+        report("conv1 fused bwd dW N%d %dx%d" % (N, H, W), rel(dw.cpu(), wr.grad), 2e-4)
+        report("conv1 fused bwd db N%d %dx%d" % (N, H, W), rel(db.cpu(), br.grad), 2e-4)
+
+
 def main():
     quick = "quick" in sys.argv
     cases = [(3, 32, 64, 128, 1), (5, 16, 128, 256, 2), (9, 8, 256, 512, 3), (25, 4, 512, 512, 4), (2, 16, 64, 64, 5)]
     if not quick:
         cases += [(200, 32, 64, 128, 6), (200, 4, 512, 512, 7), (200, 8, 512, 512, 8), (25, 16, 256, 256, 9)]
-    for fn, args in [(check_weights, ()), (check_pools, ())] + [(check_conv, c) for c in cases]:
+    for fn, args in [(check_weights, ()), (check_pools, ()), (check_first, ())] + [(check_conv, c) for c in cases]:
         try:
             fn(*args)
         except Exception:

@@ -27,6 +27,10 @@ constexpr int kStages = 3;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (2 + kEpiWarps) * 32;          // 320
 constexpr int BKP = 64;                                  // K elements (bf16) per K block = one 128-byte swizzled row
+#ifndef CLB_PLANES_CHUNK
+#define CLB_PLANES_CHUNK 16
+#endif
+constexpr int kChunk = CLB_PLANES_CHUNK;                 // K blocks chained into one TMEM accumulator before it is drained to registers
 constexpr int kTileBytes = 128 * 128;                    // 128 rows x 64 bf16
 constexpr int kStageBytes = 4 * kTileBytes;              // A_hi, A_lo, B_hi, B_lo (BN <= 128)
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
@@ -190,12 +194,8 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     } else if (warp == 1) {
         // ================================================================================ MMA issuer
         if (lane == 0) {
-            uint32_t it = 0, tcount = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++tcount) {
-                const uint32_t as = tcount & 1u;
-                mbar_wait_wd(acc_empty + 8 * as, ((tcount >> 1) & 1u) ^ 1u);
-                tc_fence_after();
-                const uint32_t d_main = tmem + as * kAccCols, d_cross = d_main + BN;
+            uint32_t it = 0, ccount = 0;                  // ccount: accumulator chunks issued so far (chunk c uses set c & 1)
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 int nkb;
                 uint32_t idesc;
                 if (KIND == 0) {
@@ -207,7 +207,16 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     nkb = min(kb0 + p.kb_per_split, p.n_kb_total) - kb0;
                     idesc = idesc_bf16((2 * nt + 1 < p.ncb) ? 128 : 64, true);
                 }
+                uint32_t d_main = 0, d_cross = 0;
                 for (int i = 0; i < nkb; ++i, ++it) {
+                    const int ic = i % kChunk;                        // position inside the accumulator chunk
+                    if (ic == 0) {
+                        const uint32_t as = ccount & 1u;
+                        mbar_wait_wd(acc_empty + 8 * as, ((ccount >> 1) & 1u) ^ 1u);
+                        tc_fence_after();
+                        d_main = tmem + as * kAccCols;
+                        d_cross = d_main + BN;
+                    }
                     const int s = it % kStages;
                     mbar_wait_wd(full + 8 * s, (it / kStages) & 1u);
                     tc_fence_after();
@@ -217,9 +226,9 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                         const uint64_t b_hi = make_desc(st + 2 * kTileBytes), b_lo = make_desc(st + 3 * kTileBytes);
 #pragma unroll
                         for (int k = 0; k < BKP / 16; ++k) {
-                            umma_bf16_ss(d_cross, a_lo + 2 * k, b_hi + 2 * k, idesc, (i | k) != 0);
+                            umma_bf16_ss(d_cross, a_lo + 2 * k, b_hi + 2 * k, idesc, (ic | k) != 0);
                             umma_bf16_ss(d_cross, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
-                            umma_bf16_ss(d_main, a_hi + 2 * k, b_hi + 2 * k, idesc, (i | k) != 0);
+                            umma_bf16_ss(d_main, a_hi + 2 * k, b_hi + 2 * k, idesc, (ic | k) != 0);
                         }
                     } else {
 #pragma unroll
@@ -228,14 +237,17 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                             const uint64_t a_hi = make_desc_mn(st + o, p.mn_lbo, p.mn_sbo), a_lo = make_desc_mn(st + kTileBytes + o, p.mn_lbo, p.mn_sbo);
                             const uint64_t b_hi = make_desc_mn(st + 2 * kTileBytes + o, p.mn_lbo, p.mn_sbo);
                             const uint64_t b_lo = make_desc_mn(st + 3 * kTileBytes + o, p.mn_lbo, p.mn_sbo);
-                            umma_bf16_ss(d_cross, a_lo, b_hi, idesc, (i | k) != 0);
+                            umma_bf16_ss(d_cross, a_lo, b_hi, idesc, (ic | k) != 0);
                             umma_bf16_ss(d_cross, a_hi, b_lo, idesc, 1);
-                            umma_bf16_ss(d_main, a_hi, b_hi, idesc, (i | k) != 0);
+                            umma_bf16_ss(d_main, a_hi, b_hi, idesc, (ic | k) != 0);
                         }
                     }
                     umma_commit(empty + 8 * s);
+                    if (ic == kChunk - 1 || i == nkb - 1) {           // chunk complete: hand it to the epilogue warps
+                        umma_commit(acc_full + 8 * (ccount & 1u));
+                        ++ccount;
+                    }
                 }
-                umma_commit(acc_full + 8 * as);
             }
         }
     } else {
@@ -243,39 +255,58 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         const int e = warp - 2, lane_grp = warp & 3, half = e >> 2;
         const int row = lane_grp * 32 + lane;
         const uint32_t lane_field = (uint32_t)(lane_grp * 32) << 16;
-        uint32_t tcount = 0;
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++tcount) {
-            const uint32_t as = tcount & 1u;
-            mbar_wait_wd(acc_full + 8 * as, (tcount >> 1) & 1u);
-            tc_fence_after();
-            const uint32_t t_main = tmem + as * kAccCols + lane_field, t_cross = t_main + BN;
+        uint32_t ccount = 0;
+        constexpr int kCols = BN / 2;                     // columns of this thread's half
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int nkb;
+            if (KIND == 0) nkb = 9 * cpb;
+            else {
+                const int kb0 = (item / (p.n_tiles_m * p.n_tiles_n)) * p.kb_per_split;
+                nkb = min(kb0 + p.kb_per_split, p.n_kb_total) - kb0;
+            }
+            // Drain every chunk of kChunk K blocks into registers with round-to-nearest fp32 adds: the TMEM accumulate
+            // truncates, and its bias grows with the number of MMAs chained into one accumulator
+            float v[kCols];
+#pragma unroll
+            for (int j = 0; j < kCols; ++j) v[j] = 0.f;
+            const int nchunks = (nkb + kChunk - 1) / kChunk;
+            for (int ch = 0; ch < nchunks; ++ch, ++ccount) {
+                const uint32_t as = ccount & 1u;
+                mbar_wait_wd(acc_full + 8 * as, (ccount >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t t_main = tmem + as * kAccCols + lane_field + (uint32_t)(half * kCols), t_cross = t_main + BN;
+#pragma unroll
+                for (int c = 0; c < kCols; c += 16) {
+                    uint32_t r[16], r2[16];
+                    tmem_ld16(t_main + (uint32_t)c, r);
+                    tmem_ld16(t_cross + (uint32_t)c, r2);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[c + j] += __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty + 8 * as);
+            }
             if (KIND == 0) {
                 const int nt = item % p.n_tiles_n, mt = item / p.n_tiles_n;
                 const int n0 = (mt / p.tg.tiles_h) * p.tg.bn, h0 = (mt % p.tg.tiles_h) * p.tg.bh;
                 const int img = n0 + (row >> p.tg.log_rows_img);
                 const int pix_in = row & ((1 << p.tg.log_rows_img) - 1);
                 const bool valid = img < p.N;
-                const size_t off = (((size_t)img * p.H + h0) * p.W + pix_in) * p.Cout + (size_t)nt * BN + half * (BN / 2);
-#pragma unroll 1
-                for (int c = 0; c < BN / 2; c += 16) {
-                    const int col = half * (BN / 2) + c;
-                    uint32_t r[16], r2[16];
-                    tmem_ld16(t_main + (uint32_t)col, r);
-                    tmem_ld16(t_cross + (uint32_t)col, r2);
-                    float v[16];
+                const size_t off = (((size_t)img * p.H + h0) * p.W + pix_in) * p.Cout + (size_t)nt * BN + half * kCols;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+                for (int c = 0; c < kCols; c += 16) {
                     if (p.bias) {
-                        const float4* bp = reinterpret_cast<const float4*>(p.bias + nt * BN + col);
+                        const float4* bp = reinterpret_cast<const float4*>(p.bias + nt * BN + half * kCols + c);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float4 b = __ldg(bp + j);
-                            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+                            v[c + 4 * j] += b.x; v[c + 4 * j + 1] += b.y; v[c + 4 * j + 2] += b.z; v[c + 4 * j + 3] += b.w;
                         }
                     }
                     if (p.relu) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                        for (int j = 0; j < 16; ++j) v[c + j] = fmaxf(v[c + j], 0.f);
                     }
                     if (valid) {
                         if (p.mask_hi) {
@@ -285,13 +316,13 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {             // bf16 > 0  <=>  sign clear and magnitude non-zero
                                 const uint32_t lo16 = mw[j] & 0xFFFFu, hi16 = mw[j] >> 16;
-                                if (!(lo16 != 0 && lo16 < 0x8000u)) v[2 * j] = 0.f;
-                                if (!(hi16 != 0 && hi16 < 0x8000u)) v[2 * j + 1] = 0.f;
+                                if (!(lo16 != 0 && lo16 < 0x8000u)) v[c + 2 * j] = 0.f;
+                                if (!(hi16 != 0 && hi16 < 0x8000u)) v[c + 2 * j + 1] = 0.f;
                             }
                         }
                         uint32_t h[8], l[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) split_pair(v[2 * j], v[2 * j + 1], h[j], l[j]);
+                        for (int j = 0; j < 8; ++j) split_pair(v[c + 2 * j], v[c + 2 * j + 1], h[j], l[j]);
                         st_global_v4(p.y_hi + off + c, h[0], h[1], h[2], h[3]);
                         st_global_v4(p.y_hi + off + c + 8, h[4], h[5], h[6], h[7]);
                         st_global_v4(p.y_lo + off + c, l[0], l[1], l[2], l[3]);
@@ -303,28 +334,13 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 const int z = item / (p.n_tiles_m * p.n_tiles_n);
                 const int ld = p.ncb * 64;                            // 9 * Cred
                 const int kout = mt * 128 + row;
-                float* dst = p.ws + ((size_t)z * p.Cout + kout) * ld + (size_t)nt * 128;
+                float* dst = p.ws + ((size_t)z * p.Cout + kout) * ld + (size_t)nt * 128 + half * 64;
                 const bool second = 2 * nt + 1 < p.ncb;
-                if (half == 0 || second) {
-#pragma unroll 1
-                    for (int c = 0; c < 64; c += 16) {
-                        const int col = half * 64 + c;
-                        uint32_t r[16], r2[16];
-                        tmem_ld16(t_main + (uint32_t)col, r);
-                        tmem_ld16(t_cross + (uint32_t)col, r2);
-                        if (kout < p.Cout) {
+                if ((half == 0 || second) && kout < p.Cout) {
 #pragma unroll
-                            for (int j = 0; j < 16; j += 4)
-                                *reinterpret_cast<float4*>(dst + col + j) =
-                                    make_float4(__uint_as_float(r[j]) + __uint_as_float(r2[j]), __uint_as_float(r[j + 1]) + __uint_as_float(r2[j + 1]),
-                                                __uint_as_float(r[j + 2]) + __uint_as_float(r2[j + 2]), __uint_as_float(r[j + 3]) + __uint_as_float(r2[j + 3]));
-                        }
-                    }
+                    for (int c = 0; c < kCols; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + 8 * as);
         }
     }
     tc_fence_before();

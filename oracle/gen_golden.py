@@ -16,6 +16,7 @@ from the reference's own functions, imported through oracle/refshim.py:
   qp       : known-answer vectors for project2cone2's QP (oracle/qp.py, cross-checked with scipy)
   ragged   : finetune / EWC / MAS again with dataset sizes that leave ragged last batches (56, 41, 18 at bs 16)
   schedule : the epoch protocol over 30 epochs without improvement (lr cut at count 5, stop at > 10; SI: >= 10)
+  wide     : EWC and SI again on a >= 64-channel net (data seeds searched for decision margins, see MarginMonitor)
   imm      : methods.IMM.merge.{diag_fisher, IMM_merge_models} (mode-IMM precision with sampled labels, mean / mode merge)
 
 Inputs are synthetic (torch.Generator seeds recorded in each fixture), the seed protocol is the
@@ -393,6 +394,128 @@ def gen_schedule(tmp):
     torch.save(out, os.path.join(GOLDEN, "schedule.pt"))
 
 
+# ---------------------------------------------------------------------------------------------- wide (>= 64 channels)
+WIDE_CFG = [64, "M", 64, 128, "M"]          # on 8x8 inputs: conv 3->64 @8x8 | pool | 64->64, 64->128 @4x4 | pool -> 128*2*2
+WIDE_HW, WIDE_BS = 8, 2
+
+
+class MarginMonitor:
+    """Smallest relative distance of any ReLU pre-activation / max-pool runner-up from its decision boundary over every
+    forward pass of a run (forward hooks on the reference model).  Gradients of a ReLU / max-pool net are discontinuous at
+    these boundaries: a fixture is only a meaningful 1e-4 parity target when no unit sits within the arithmetic error of
+    the implementations under test (~1e-5 of the layer's scale), so the generator searches data seeds for that."""
+
+    def __init__(self, model):
+        self.min_rel = float("inf")
+        mods = list(model.features) + list(model.classifier)
+        for i, m in enumerate(mods):
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            if isinstance(m, (nn.Conv2d, nn.Linear)) and isinstance(nxt, nn.ReLU):
+                m.register_forward_hook(self._relu)
+            elif isinstance(m, nn.MaxPool2d):
+                m.register_forward_hook(self._pool)
+
+    def _relu(self, mod, inp, out):
+        z = out.detach().abs()
+        self.min_rel = min(self.min_rel, float(z.min() / z.max()))
+
+    def _pool(self, mod, inp, out):
+        x = inp[0].detach()
+        win = x.unfold(2, 2, 2).unfold(3, 2, 2).reshape(x.shape[0], x.shape[1], -1, 4)
+        top = win.topk(2, dim=-1).values
+        live = top[..., 0] > 0
+        if live.any():
+            self.min_rel = min(self.min_rel, float((top[..., 0] - top[..., 1])[live].min() / x.max()))
+
+
+def new_wide_model():
+    import models.VGGSlim as V
+    import utilities.utils as U
+    V.cfg["wide"] = WIDE_CFG
+    U.set_random(7)
+    return V.VGGSlim(config="wide", num_classes=NCLS, classifier_inputdim=128 * 2 * 2, classifier_dim1=32, classifier_dim2=32)
+
+
+def _wide_task(seed, n):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(n, 3, WIDE_HW, WIDE_HW, generator=g), torch.randint(0, NCLS, (n,), generator=g)
+
+
+def _wide_loaders(seed):
+    xt, yt = _wide_task(seed, 4)
+    xv, yv = _wide_task(seed + 1000, 2)
+    mk = lambda x, y: torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=WIDE_BS, shuffle=False)
+    return {"train": mk(xt, yt), "val": mk(xv, yv)}, {"train": 4, "val": 2}, (xt, yt, xv, yv)
+
+
+def _wide_ewc(tmp, seed):
+    import methods.EWC.main_EWC as M
+    import methods.EWC.train_EWC as T
+    model = new_wide_model()
+    mon = MarginMonitor(model)
+    init = sd(model)
+    xp, yp = _wide_task(seed, 4)
+    dpath = os.path.join(tmp, "wide_prev.pth")
+    save_dsets(dpath, xp, yp)
+    with quiet():
+        model = M.accumulate_EWC_weights(None, [dpath], model, WIDE_BS)
+    model.reg_params["lambda"] = 50.0
+    reg_after_pass = reg_dump(model, ("omega", "init_val"))
+    torch.manual_seed(500)
+    model.classifier._modules["4"] = nn.Linear(32, NCLS)
+    head = {k: v.clone() for k, v in model.classifier._modules["4"].state_dict().items()}
+    loaders, sizes, data = _wide_loaders(seed + 1)
+    crit = RecCE()
+    opt = T.Weight_Regularized_SGD(model.parameters(), 0.05, momentum=0.9, weight_decay=1e-4)
+    with quiet():
+        model, best = T.train_model(model, crit, opt, 0.05, loaders, sizes, False, 1, exp_dir=tmp + "/", resume="")
+    return mon.min_rel, dict(init=init, prev_data=(xp, yp), data=data, lam=50.0, lr=0.05, wd=1e-4, epochs=1, seed=seed,
+                             reg_after_pass=reg_after_pass, new_head=head, final=sd(model), best_acc=float(best),
+                             losses=crit.losses)
+
+
+def _wide_si(tmp, seed):
+    import methods.SI.train_SI as T
+    model = new_wide_model()
+    mon = MarginMonitor(model)
+    init = sd(model)
+    with quiet():
+        reg = T.initialize_reg_params(model)
+    reg["lambda"] = 2.0
+    model.reg_params = reg
+    with torch.no_grad():                                  # a non-trivial omega / theta* so that the penalty is active
+        g = torch.Generator().manual_seed(seed + 7)
+        for p in model.parameters():
+            reg[p]["omega"] = torch.rand(p.shape, generator=g)
+            reg[p]["init_val"] = p.data + 0.01 * torch.randn(p.shape, generator=g)
+    reg_before = reg_dump(model)
+    loaders, sizes, data = _wide_loaders(seed + 1)
+    crit = RecCE()
+    opt = T.Elastic_SGD(model.parameters(), 0.05, momentum=0.9, weight_decay=0.0)
+    with quiet():
+        model, best = T.train_model(model, crit, opt, 0.05, loaders, sizes, False, 1, exp_dir=tmp + "/", resume="")
+    return mon.min_rel, dict(init=init, data=data, lam=2.0, lr=0.05, epochs=1, seed=seed, reg_before=reg_before,
+                             reg_after=reg_dump(model), final=sd(model), best_acc=float(best), losses=crit.losses)
+
+
+def gen_wide(tmp, want=2e-5, max_seeds=4000):
+    """EWC (Fisher pass + penalised training) and SI (path integral) on a >= 64-channel VGGSlim, so that the fixture
+    exercises the layers the tensor-core kernels take; data seeds searched for decision margins (MarginMonitor)."""
+    out = {}
+    for name, fn in (("ewc", _wide_ewc), ("si", _wide_si)):
+        best = (0.0, None)
+        for seed in range(9000, 9000 + max_seeds):
+            rel, fx = fn(tmp, seed)
+            if rel > best[0]:
+                best = (rel, fx)
+            if rel >= want:
+                break
+        out[name] = best[1]
+        out[name]["min_margin"] = best[0]
+        print("wide/%s: seed %d, smallest decision margin %.2e" % (name, best[1]["seed"], best[0]))
+    torch.save(out, os.path.join(GOLDEN, "wide.pt"))
+
+
 def gen_qp():
     import scipy.optimize as so
     from oracle import qp
@@ -422,12 +545,13 @@ def main():
     refshim.install()
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(1)                                # fixed reduction order for the fixtures
-    if len(sys.argv) > 1 and sys.argv[1] in ("ragged", "imm", "schedule"):   # add one fixture without touching the others
+    if len(sys.argv) > 1 and sys.argv[1] in ("ragged", "imm", "schedule", "wide"):   # add one fixture without touching the others
         with tempfile.TemporaryDirectory() as tmp:
-            {"ragged": gen_ragged, "imm": gen_imm, "schedule": gen_schedule}[sys.argv[1]](tmp)
+            {"ragged": gen_ragged, "imm": gen_imm, "schedule": gen_schedule, "wide": gen_wide}[sys.argv[1]](tmp)
         print(sys.argv[1] + ".pt", os.path.getsize(os.path.join(GOLDEN, sys.argv[1] + ".pt")))
         return
     with tempfile.TemporaryDirectory() as tmp:
+        gen_wide(tmp)
         gen_ragged(tmp)
         gen_imm(tmp)
         gen_schedule(tmp)

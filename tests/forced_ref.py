@@ -1,0 +1,112 @@
+"""Test helper: an fp64 evaluation of a VGG-style model that takes the ReLU / max-pool DECISIONS of an engine run.
+
+Why: gradients of a ReLU / max-pool net are discontinuous at ReLU zeros and pool ties, so two correct evaluations in
+different arithmetic (torch-CPU fp32, cuDNN, this engine) differ by O(1/sqrt(#units)) as soon as ONE unit with a
+pre-activation inside the rounding error lands on the other side -- which is certain on the BASELINE-size nets (~5 M
+units per batch).  Round 1 therefore held the full-size nets to a 1e-1 bound.  This helper splits the comparison into two
+statements that CAN be held tightly:
+  (1) decisions: every ReLU mask / pool arg-max of the engine equals the one of the fp64 evaluation of the SAME layer
+      input, except for units whose fp64 margin is below `flip_tol` (relative to the layer's largest |value|) -- the
+      returned audit lists the count and the largest margin of such units;
+  (2) given those decisions, logits, loss and every parameter gradient agree with fp64 to 1e-4 (north_star).
+Only tests import this module."""
+import torch
+import torch.nn.functional as F
+
+
+def _planes_to_nchw(pl, n, H, W, C):
+    hi = pl[0][:n * H * W * C].view(torch.bfloat16).float()
+    lo = pl[1][:n * H * W * C].view(torch.bfloat16).float()
+    return (hi + lo).view(n, H, W, C).permute(0, 3, 1, 2)
+
+
+def _audit(audit, name, wrong, margin_rel):
+    k = int(wrong.sum().item())
+    audit["decisions"] += wrong.numel()
+    if k:
+        audit["flips"] += k
+        audit["max_flip_margin"] = max(audit["max_flip_margin"], float(margin_rel[wrong].max().item()))
+        audit["layers"][name] = audit["layers"].get(name, 0) + k
+
+
+def forced_reference(eng, x, y, loss_mode, denom=None, device="cpu"):
+    """Re-evaluate eng.model in fp64 on `device` with the decisions of the engine's LAST forward on (x, y).
+    Returns (logits, loss, [grad per parameter], audit)."""
+    dt = torch.float64
+    n = x.shape[0]
+    params = [p.detach().to(device, dt).requires_grad_(True) for p in eng.params]
+    a = x.detach().to(device, dt)
+    audit = dict(decisions=0, flips=0, max_flip_margin=0.0, layers={})
+    ops = eng.ops
+    i = 0
+    while i < len(ops):
+        op = ops[i]
+        k = op["kind"]
+        if k == "conv":
+            assert op["relu"], "forced_reference: conv without ReLU"
+            z = F.conv2d(a, params[op["w"]], params[op["b"]] if op["b"] is not None else None, stride=op["stride"], padding=op["pad"])
+            scale = z.detach().abs().max()
+            nxt = ops[i + 1] if i + 1 < len(ops) else None
+            if nxt is not None and nxt["kind"] == "maxpool" and (op.get("fused_first") or op.get("transient")):
+                # conv + ReLU + 2x2 pool: the engine keeps (arg-max, pooled value); pooled > 0 <=> ReLU of the winner is on
+                K, PH, PW = nxt["out_shape"]
+                am = nxt["argmax"][:n * PH * PW * K].view(n, PH, PW, K).permute(0, 3, 1, 2).to(device).long()
+                if nxt.get("lay_out") == "planes":
+                    pooled_gpu = _planes_to_nchw(nxt["out_pl"], n, PH, PW, K).to(device)
+                else:
+                    pooled_gpu = nxt["out"][:n * K * PH * PW].view(n, K, PH, PW).to(device)
+                live = pooled_gpu > 0
+                win = z.unfold(2, 2, 2).unfold(3, 2, 2).reshape(n, K, PH, PW, 4)
+                chosen = win.gather(-1, am.unsqueeze(-1)).squeeze(-1)
+                wd = win.detach()
+                best, best_i = torch.relu(wd).max(-1)
+                # first-maximum-wins like ATen: torch.max returns the first index among equal values
+                gap = (best - torch.relu(wd.gather(-1, am.unsqueeze(-1)).squeeze(-1))) / scale
+                _audit(audit, "pool%d" % (i + 1), (best_i != am) & (best > 0), gap)
+                _audit(audit, "relu%d" % i, (chosen.detach() > 0) != live, chosen.detach().abs() / scale)
+                a = chosen * live.to(dt)
+                i += 2
+                continue
+            if op.get("planes"):
+                mask = _planes_to_nchw(op["out_pl"], n, op["H"], op["W"], op["K"]).to(device) > 0
+            else:
+                mask = op["out"][:n * op["out_numel"]].view(n, *op["out_shape"]).to(device) > 0
+            _audit(audit, "relu%d" % i, (z.detach() > 0) != mask, z.detach().abs() / scale)
+            a = z * mask.to(dt)
+        elif k == "maxpool":
+            # stand-alone pool over an fp32 NCHW activation (legacy layers): decisions from the stored arg-max
+            K, PH, PW = op["out_shape"]
+            kk, st = op["k"], op["stride"]
+            am = op["argmax"][:n * K * PH * PW].view(n, K, PH, PW).to(device).long()
+            win = a.unfold(2, kk, st).unfold(3, kk, st).reshape(n, K, PH, PW, kk * kk)
+            best, best_i = win.detach().max(-1)
+            sc = a.detach().abs().max().clamp_min(1e-300)
+            gap = (best - win.detach().gather(-1, am.unsqueeze(-1)).squeeze(-1)) / sc
+            _audit(audit, "pool%d" % i, best_i != am, gap)
+            a = win.gather(-1, am.unsqueeze(-1)).squeeze(-1)
+        elif k == "linear":
+            z = a.reshape(n, -1) @ params[op["w"]].t()
+            if op["b"] is not None:
+                z = z + params[op["b"]]
+            if op["relu"]:
+                mask = op["out"][:n * op["outf"]].view(n, op["outf"]).to(device) > 0
+                scale = z.detach().abs().max()
+                _audit(audit, "fc%d" % i, (z.detach() > 0) != mask, z.detach().abs() / scale)
+                a = z * mask.to(dt)
+            else:
+                a = z
+        elif k == "dropout":
+            pass                                                     # eval-mode passes only
+        else:
+            raise NotImplementedError(k)
+        i += 1
+    logits = a
+    yy = y.to(device)
+    if loss_mode == 0:
+        loss = F.cross_entropy(logits, yy, reduction="sum") / float(n if denom is None else denom)
+    elif loss_mode == 1:
+        loss = F.cross_entropy(logits, yy, reduction="sum")
+    else:
+        loss = (logits ** 2).sum()
+    grads = torch.autograd.grad(loss, params, allow_unused=True)
+    return logits.detach(), float(loss.item()), [g if g is not None else torch.zeros_like(p) for g, p in zip(grads, params)], audit

@@ -12,7 +12,7 @@ import pytest
 import torch
 import torch.nn as nn
 
-from tests.util import BS, NCLS, load_golden, loaders, rel_err, tiny_model
+from tests.util import BS, NCLS, WIDE_BS, WIDE_HW, load_golden, loaders, rel_err, tiny_model, wide_model
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -156,3 +156,138 @@ def test_gem_observe(tmp_path):
     assert torch.equal(net.memory_labels, g["memory_labels"])                              # ring buffer: bit-exact
     for t in range(g["n_tasks"]):
         assert net.memory_data[t] == g["exemplars"][t]
+
+
+# ---------------------------------------------------------------------------------------------- ragged tails / epoch protocol
+def _one_penalty_round(which, r, m, tmp_path, bs, hw, n_train_batches, n_val_batches, loss_rtol=1e-5):
+    """importance pass on the previous task's data, fresh head, penalised train_model -- one round of a fixture"""
+    if which == "ewc":
+        from clsurvey_b200.methods.EWC import main_EWC as M, train_EWC as T
+        accumulate = lambda model, ds: M.accumulate_EWC_weights(None, [ds], model, bs)
+    else:
+        from clsurvey_b200.methods.MAS import main_MAS as M, train_MAS as T
+        accumulate = lambda model, ds: M.accumulate_objective_based_weights(None, [ds], model, bs, "L2", "train")
+    from clsurvey_b200.engine import get_engine
+    from clsurvey_b200.methods import trainers
+    get_engine(m, (3, hw, hw), bs)
+    xp, yp = r["prev_data"]
+    m = accumulate(m, _dsets(xp, yp))
+    m.reg_params["lambda"] = r["lam"]
+    named = dict(m.named_parameters())
+    for n, ref in r["reg_after_pass"].items():
+        assert rel_err(m.reg_params[named[n]]["omega"], ref["omega"]) <= TOL, (which, n, "omega")
+        assert rel_err(m.reg_params[named[n]]["init_val"], ref["init_val"]) <= TOL, (which, n, "init_val")
+    m.classifier._modules["4"] = nn.Linear(32, NCLS)
+    m.classifier._modules["4"].load_state_dict(r["new_head"])
+    get_engine(m).bind(m)
+    ld, sizes = loaders(r["data"], bs)
+    opt = T.Weight_Regularized_SGD(m.parameters(), r["lr"], momentum=0.9, weight_decay=r["wd"])
+    m, best = T.train_model(m, nn.CrossEntropyLoss(), opt, r["lr"], ld, sizes, True, r["epochs"], exp_dir=str(tmp_path), resume="")
+    assert best == r["best_acc"], (which, best, r["best_acc"])
+    ref = _train_losses(r["losses"], r["epochs"], n_train_batches, n_val_batches)
+    assert np.allclose(trainers.LAST_RUN["batch_losses"], ref, rtol=loss_rtol, atol=0), which
+    for k, v in r["final"].items():
+        assert rel_err(m.state_dict()[k], v) <= TOL, (which, k)
+    return m
+
+
+def test_ragged_tails(tmp_path):
+    """Dataset sizes that leave ragged last batches (importance pass 56 = 16,16,16,8 -- MAS's running mean uses the CURRENT
+    batch size, train_MAS.py:168-173 --, training 41 = 16,16,9, validation 18 = 16,2): tests/golden/ragged.pt."""
+    from clsurvey_b200.engine import Engine
+    from clsurvey_b200.methods import trainers
+    from clsurvey_b200.methods.Finetune import train_SGD
+    from clsurvey_b200.methods.optim import SGD
+    g = load_golden("ragged")
+    f = g["finetune"]
+    m = tiny_model(f["init"])
+    Engine(m, (3, 16, 16), BS)
+    ld, sizes = loaders(f["data"])
+    opt = SGD(m.parameters(), f["lr"], momentum=0.9, weight_decay=f["wd"])
+    m, best = train_SGD.train_model(m, nn.CrossEntropyLoss(), opt, f["lr"], ld, sizes, True, f["epochs"], exp_dir=str(tmp_path),
+                                    resume="", save_models_mode=False)
+    assert best == f["best_acc"]
+    assert np.allclose(trainers.LAST_RUN["batch_losses"], _train_losses(f["losses"], f["epochs"], 3, 2), rtol=1e-5, atol=0)
+    for k, v in f["final"].items():
+        assert rel_err(m.state_dict()[k], v) <= TOL, ("finetune", k)
+    for which in ("ewc", "mas"):
+        _one_penalty_round(which, g[which], tiny_model(g[which]["init"]), tmp_path, BS, 16, 3, 2)
+
+
+@pytest.mark.parametrize("which", ["sgd", "ewc", "si", "sgd_short", "diverge_ewc", "diverge_si", "diverge_sgd"])
+def test_epoch_protocol(which, tmp_path):
+    """Long runs without improvement: lr cut at val_beat_counts == 5, stop at > 10 (Finetune train_SGD.py:10-30, EWC
+    train_EWC.py:89-101) resp. >= 10 with the num_epochs + 1 range (SI train_SI.py:129-141,182); divergence: EWC / SI abort
+    when the epoch loss exceeds 1e4 or is NaN (train_EWC.py:204-205, train_SI.py:242-244), Finetune keeps going."""
+    from clsurvey_b200.engine import get_engine
+    from clsurvey_b200.methods import trainers
+    from clsurvey_b200.methods.EWC import train_EWC as TE
+    from clsurvey_b200.methods.Finetune import train_SGD
+    from clsurvey_b200.methods.SI import train_SI as TI
+    from clsurvey_b200.methods.optim import SGD
+    sch = load_golden("schedule")
+    ld, sizes = loaders(sch["data"])
+    r = sch[which]
+    m = tiny_model(sch["init"])
+    get_engine(m, (3, 16, 16), BS)
+    tmp = str(tmp_path)
+    if which.endswith("sgd") or which == "sgd_short":
+        opt = SGD(m.parameters(), r["lr"], momentum=0.9, weight_decay=0.0)
+        m, best = train_SGD.train_model(m, nn.CrossEntropyLoss(), opt, r["lr"], ld, sizes, True, r["epochs"], exp_dir=tmp,
+                                        resume="", save_models_mode=False)
+    elif which.endswith("ewc"):
+        m.reg_params = {p: dict(omega=torch.ones_like(p), init_val=p.data.clone()) for p in m.parameters()}
+        m.reg_params["lambda"] = 1.0
+        opt = TE.Weight_Regularized_SGD(m.parameters(), r["lr"], momentum=0.9, weight_decay=0.0)
+        m, best = TE.train_model(m, nn.CrossEntropyLoss(), opt, r["lr"], ld, sizes, True, r["epochs"], exp_dir=tmp, resume="")
+    else:
+        reg = TI.initialize_reg_params(m)
+        reg["lambda"] = 1.0
+        m.reg_params = reg
+        opt = TI.Elastic_SGD(m.parameters(), r["lr"], momentum=0.9, weight_decay=0.0)
+        m, best = TI.train_model(m, nn.CrossEntropyLoss(), opt, r["lr"], ld, sizes, True, r["epochs"], exp_dir=tmp, resume="")
+    n_calls = sum(len(ld[phase]) for _, phase, _, _ in trainers.LAST_RUN["epochs"])
+    assert n_calls == r["n_criterion_calls"], (which, n_calls, r["n_criterion_calls"])
+    assert abs(opt.param_groups[0]["lr"] - r["final_lr"]) <= 1e-12 * r["final_lr"], (which, opt.param_groups[0]["lr"])
+    assert best == r["best_acc"], (which, best, r["best_acc"])
+
+
+# ---------------------------------------------------------------------------------------------- >= 64 channels (planes kernels)
+def test_wide_ewc_through_planes_kernels(tmp_path):
+    """tests/golden/wide.pt: the UNMODIFIED reference's EWC round (diag_fisher + Weight_Regularized_SGD training) on a 64 /
+    64 / 128-channel VGGSlim -- every conv runs on the kernels bench.py times (fused first layer, TMA-fed tcgen05 convs)."""
+    from clsurvey_b200.engine import get_engine
+    r = load_golden("wide")["ewc"]
+    m = wide_model(r["init"])
+    eng = get_engine(m, (3, WIDE_HW, WIDE_HW), WIDE_BS)
+    assert eng.ops[0].get("fused_first") and sum(1 for op in eng.ops if op.get("planes")) == 2, "planes pipeline not active"
+    _one_penalty_round("ewc", r, m, tmp_path, WIDE_BS, WIDE_HW, 2, 1, loss_rtol=TOL)    # tensor-core layers: north_star 1e-4
+
+
+def test_wide_si_through_planes_kernels(tmp_path):
+    from clsurvey_b200.engine import get_engine
+    from clsurvey_b200.methods import trainers
+    from clsurvey_b200.methods.SI import train_SI as T
+    r = load_golden("wide")["si"]
+    m = wide_model(r["init"])
+    eng = get_engine(m, (3, WIDE_HW, WIDE_HW), WIDE_BS)
+    assert eng.ops[0].get("fused_first") and sum(1 for op in eng.ops if op.get("planes")) == 2, "planes pipeline not active"
+    reg = T.initialize_reg_params(m)
+    reg["lambda"] = r["lam"]
+    m.reg_params = reg
+    named = dict(m.named_parameters())
+    with torch.no_grad():
+        for n, ref in r["reg_before"].items():
+            reg[named[n]]["omega"].copy_(ref["omega"])
+            reg[named[n]]["init_val"].copy_(ref["init_val"])
+    ld, sizes = loaders(r["data"], WIDE_BS)
+    opt = T.Elastic_SGD(m.parameters(), r["lr"], momentum=0.9, weight_decay=0.0)
+    m, best = T.train_model(m, nn.CrossEntropyLoss(), opt, r["lr"], ld, sizes, True, r["epochs"], exp_dir=str(tmp_path), resume="")
+    assert best == r["best_acc"]
+    assert len(trainers.LAST_RUN["batch_losses"]) == (r["epochs"] + 1) * len(ld["train"])
+    ref_losses = [l for e in range(r["epochs"] + 1) for l in r["losses"][e * 3: e * 3 + 2]]
+    assert np.allclose(trainers.LAST_RUN["batch_losses"], ref_losses, rtol=TOL, atol=0)
+    for k, v in r["final"].items():
+        assert rel_err(m.state_dict()[k], v) <= TOL, k
+    for n, ref in r["reg_after"].items():
+        assert rel_err(m.reg_params[named[n]]["w"], ref["w"]) <= 2e-3, n

@@ -22,6 +22,17 @@ def tiny_model(state=None, dropout=False, num_classes=NCLS):
     return m
 
 
+WIDE_CFG = [64, "M", 64, 128, "M"]       # tests/golden/wide.pt: 8x8 inputs, batch 2 (oracle/gen_golden.py gen_wide)
+WIDE_HW, WIDE_BS = 8, 2
+
+
+def wide_model(state=None, num_classes=NCLS):
+    m = VGGSlim(WIDE_CFG, num_classes, 128 * 2 * 2, 32, 32)
+    if state is not None:
+        m.load_state_dict(state)
+    return m
+
+
 def loaders(data, bs=BS):
     xt, yt, xv, yv = data
     mk = lambda x, y: torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=bs, shuffle=False)

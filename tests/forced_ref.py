@@ -95,6 +95,8 @@ def forced_reference(eng, x, y, loss_mode, denom=None, device="cpu"):
                 a = z * mask.to(dt)
             else:
                 a = z
+        elif k == "avgpool":
+            a = F.adaptive_avg_pool2d(a, (op["OH"], op["OW"]))
         elif k == "dropout":
             pass                                                     # eval-mode passes only
         else:

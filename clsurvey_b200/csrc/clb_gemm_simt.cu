@@ -393,12 +393,22 @@ static void conv_bias_grad_finish(const float* scratch, float* db, int N, int K,
     conv_bias_grad_final_kernel<<<(K + 127) / 128, 128, 0, s>>>(scratch, db, K, nsplit); clb::count_launch();
 }
 
-__global__ void linear_bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ db, int M, int out) {
-    const int o = blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= out) return;
+// db[o] = sum_m dy[m][o]: one CTA of 32 x 8 threads per 32 outputs (lanes along o: coalesced rows; the 8 row groups are added
+// in a fixed order: deterministic)
+__global__ void __launch_bounds__(256) linear_bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ db, int M, int out) {
+    __shared__ float red[8][33];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int o = blockIdx.x * 32 + lane;
     float s = 0.f;
-    for (int m = 0; m < M; ++m) s += dy[(int64_t)m * out + o];
-    db[o] = s;
+    if (o < out)
+        for (int m = grp; m < M; m += 8) s += dy[(int64_t)m * out + o];
+    red[grp][lane] = s;
+    __syncthreads();
+    if (grp == 0 && o < out) {
+        float t = red[0][lane];
+        for (int g = 1; g < 8; ++g) t += red[g][lane];
+        db[o] = t;
+    }
 }
 
 // wt[c][k][R-1-r][S-1-s] = w[k][c][r][s]   (dgrad as a forward conv of dY)
@@ -686,7 +696,7 @@ int clb_linear_wgrad(const float* x, const float* dy, float* dw, float* dbias, f
         if (rc) return rc;
         CLB_CHECK_LAUNCH();
         if (dbias) {
-            linear_bias_grad_kernel<<<(out + 127) / 128, 128, 0, s>>>(dy, dbias, M, out); clb::count_launch();
+            linear_bias_grad_kernel<<<(out + 31) / 32, 256, 0, s>>>(dy, dbias, M, out); clb::count_launch();
             CLB_CHECK_LAUNCH();
         }
         return CLB_OK;
@@ -703,7 +713,7 @@ int clb_linear_wgrad(const float* x, const float* dy, float* dw, float* dbias, f
     }
     CLB_CHECK_LAUNCH();
     if (dbias) {
-        linear_bias_grad_kernel<<<(out + 127) / 128, 128, 0, s>>>(dy, dbias, M, out); clb::count_launch();
+        linear_bias_grad_kernel<<<(out + 31) / 32, 256, 0, s>>>(dy, dbias, M, out); clb::count_launch();
         CLB_CHECK_LAUNCH();
     }
     return CLB_OK;

@@ -14,14 +14,21 @@ namespace pl {
 
 constexpr int kF1K = 64, kF1Taps = 27;
 
-// tile[c][i][1 + w]: input rows 2ph-1 .. 2ph+2 of the three channels, zero padded; row pitch W + 4 (16-byte multiple)
-__device__ __forceinline__ void load_tile(const float* __restrict__ x, float* tile, int n, int ph, int H, int W, int pitch) {
+// tile[c][i][1 + w]: input rows 2ph-1 .. 2ph+2 of the three channels, zero padded; row pitch W + 4 (16-byte multiple).
+// Loaded with cp.async (zero fill outside the image) into one of two buffers, so that the tile of the CTA's next row
+// streams in underneath the arithmetic of the current one.
+__device__ __forceinline__ void load_tile_async(const float* __restrict__ x, float* tile, int n, int ph, int H, int W, int pitch) {
     for (int i = threadIdx.x; i < 3 * 4 * pitch; i += blockDim.x) {
         const int col = i % pitch, row = (i / pitch) & 3, c = i / (4 * pitch);
         const int h = 2 * ph - 1 + row, w = col - 1;
-        tile[i] = ((unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W) ? __ldg(x + (((int64_t)n * 3 + c) * H + h) * W + w) : 0.f;
+        const bool ok = (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W;
+        const float* src = ok ? x + (((int64_t)n * 3 + c) * H + h) * W + w : x;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile + i);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(ok ? 4 : 0) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void wait_tile() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // thread = 8 filters (kq = lane & 7) of one pooled pixel (pw = 4 * warp + (lane >> 3), + 32 per pass): the 8 x 16-byte
 // stores of a pixel are one contiguous 128-byte line per plane
@@ -31,7 +38,8 @@ __global__ void __launch_bounds__(256, 2) conv1_pool_fwd_kernel(const float* __r
     extern __shared__ float sm[];
     const int PH = H >> 1, PW = W >> 1, pitch = W + 4;
     float* w_s = sm;                                  // [27][64]
-    float* tile = sm + kF1Taps * kF1K;                // [3][4][pitch]
+    float* tiles = sm + kF1Taps * kF1K;               // 2 x [3][4][pitch]
+    const int tile_elems = 12 * pitch;
     for (int i = threadIdx.x; i < kF1Taps * kF1K; i += blockDim.x) {
         const int k = i & 63, t = i >> 6;             // w[k][c][r][s], t = c * 9 + r * 3 + s
         w_s[i] = __ldg(w + k * kF1Taps + t);
@@ -40,11 +48,15 @@ __global__ void __launch_bounds__(256, 2) conv1_pool_fwd_kernel(const float* __r
     float b8[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) b8[j] = bias ? __ldg(bias + kq * 8 + j) : 0.f;
-    for (int row = blockIdx.x; row < N * PH; row += gridDim.x) {
+    int buf = 0;
+    if ((int)blockIdx.x < N * PH) load_tile_async(x, tiles, blockIdx.x / PH, blockIdx.x % PH, H, W, pitch);
+    for (int row = blockIdx.x; row < N * PH; row += gridDim.x, buf ^= 1) {
         const int n = row / PH, ph = row - n * PH;
-        __syncthreads();
-        load_tile(x, tile, n, ph, H, W, pitch);
-        __syncthreads();
+        const float* tile = tiles + buf * tile_elems;
+        wait_tile();
+        __syncthreads();                              // this row's tile is complete; everyone is done with the other buffer
+        const int nrow = row + gridDim.x;
+        if (nrow < N * PH) load_tile_async(x, tiles + (buf ^ 1) * tile_elems, nrow / PH, nrow % PH, H, W, pitch);
         for (int pw = pwl; pw < PW; pw += 32) {
             float acc[4][8];
 #pragma unroll
@@ -108,8 +120,9 @@ __global__ void __launch_bounds__(256) conv1_pool_bwd_kernel(const float* __rest
                                                              int rows_per_cta) {
     extern __shared__ float sm[];
     const int PH = H >> 1, PW = W >> 1, pitch = W + 4;
-    float* tile = sm;                                 // [3][4][pitch]
-    float* red = sm + 3 * 4 * pitch;                  // [64][28]
+    float* tiles = sm;                                // 2 x [3][4][pitch]
+    const int tile_elems = 12 * pitch;
+    float* red = sm + 2 * tile_elems;                 // [64][28]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float acc[2][28];
 #pragma unroll
@@ -117,11 +130,14 @@ __global__ void __launch_bounds__(256) conv1_pool_bwd_kernel(const float* __rest
 #pragma unroll
         for (int t = 0; t < 28; ++t) acc[q][t] = 0.f;
     const int row0 = blockIdx.x * rows_per_cta, row1 = min(N * PH, row0 + rows_per_cta);
-    for (int row = row0; row < row1; ++row) {
+    int buf = 0;
+    if (row0 < row1) load_tile_async(x, tiles, row0 / PH, row0 % PH, H, W, pitch);
+    for (int row = row0; row < row1; ++row, buf ^= 1) {
         const int n = row / PH, ph = row - n * PH;
+        const float* tile = tiles + buf * tile_elems;
+        wait_tile();
         __syncthreads();
-        load_tile(x, tile, n, ph, H, W, pitch);
-        __syncthreads();
+        if (row + 1 < row1) load_tile_async(x, tiles + (buf ^ 1) * tile_elems, (row + 1) / PH, (row + 1) % PH, H, W, pitch);
         for (int pw = warp; pw < PW; pw += 8) {
             const int64_t o = (((int64_t)n * PH + ph) * PW + pw) * kF1K + 2 * lane;
             const uint32_t h2 = __ldg(reinterpret_cast<const uint32_t*>(dp_hi + o)), l2 = __ldg(reinterpret_cast<const uint32_t*>(dp_lo + o));
@@ -200,7 +216,7 @@ bool first_supported(int C, int H, int W, int K, int R, int S, int stride, int p
 }
 int conv1_pool_fwd(const float* x, const float* w, const float* bias, uint16_t* y_hi, uint16_t* y_lo, uint8_t* am, int N, int H, int W,
                    cudaStream_t s) {
-    const size_t smem = (size_t)(kF1Taps * kF1K + 12 * (W + 4)) * 4;
+    const size_t smem = (size_t)(kF1Taps * kF1K + 2 * 12 * (W + 4)) * 4;
     int grid = N * (H / 2);
     if (grid > sm_count() * 6) grid = sm_count() * 6;
     conv1_pool_fwd_kernel<<<grid, 256, smem, s>>>(x, w, bias, y_hi, y_lo, am, N, H, W); clb::count_launch();
@@ -211,7 +227,7 @@ int conv1_pool_bwd(const float* x, const uint16_t* dp_hi, const uint16_t* dp_lo,
                    float* db, float* part, int N, int H, int W, cudaStream_t s) {
     const int rows = N * (H / 2);
     const int per = (rows + kF1Ctas - 1) / kF1Ctas, ctas = (rows + per - 1) / per;
-    const size_t smem = (size_t)(12 * (W + 4) + kF1K * 28) * 4;
+    const size_t smem = (size_t)(2 * 12 * (W + 4) + kF1K * 28) * 4;
     conv1_pool_bwd_kernel<<<ctas, 256, smem, s>>>(x, dp_hi, dp_lo, pooled_hi, am, part, N, H, W, per); clb::count_launch();
     conv1_bwd_final_kernel<<<(kF1K * 28 + 7) / 8, 256, 0, s>>>(part, dw, db, ctas); clb::count_launch();
     return CLB_OK;

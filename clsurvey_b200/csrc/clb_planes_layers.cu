@@ -354,10 +354,16 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
         const int k = (int)(g / cg), c0 = (int)(g - (int64_t)k * cg) * 32;
         const float* src = ws + ((int64_t)k * 9) * C + c0 + lane;
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            float s = src[(int64_t)t * C];
-            for (int z = 1; z < splits; ++z) s += src[(int64_t)z * total + (int64_t)t * C];
-            buf[warp][lane * 9 + t] = s;
+        for (int t = 0; t < 9; ++t) {                 // four interleaved partial sums: loads in flight, order still fixed
+            const float* q = src + (int64_t)t * C;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            int z = 0;
+            for (; z + 4 <= splits; z += 4) {
+                a0 += q[(int64_t)z * total]; a1 += q[(int64_t)(z + 1) * total];
+                a2 += q[(int64_t)(z + 2) * total]; a3 += q[(int64_t)(z + 3) * total];
+            }
+            for (; z < splits; ++z) a0 += q[(int64_t)z * total];
+            buf[warp][lane * 9 + t] = (a0 + a1) + (a2 + a3);
         }
         __syncwarp();
         const int64_t o0 = ((int64_t)k * C + c0) * 9;

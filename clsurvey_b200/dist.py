@@ -148,6 +148,41 @@ def allreduce_grads(engine):
     engine.n_launch += 1
 
 
+def broadcast_flat(t, src=0):
+    """Rank `src`'s copy of a flat tensor to every rank (replica initialisation; torch.distributed plumbing)."""
+    if _state["world"] <= 1:
+        return
+    import torch.distributed as td
+    td.broadcast(t, src=src)
+
+
+def sync_replicas(engine):
+    """Data parallelism assumes bit-identical replicas: broadcast rank 0's parameters and optimiser / importance state
+    (fresh heads come from each rank's host generator; nothing else guarantees that they agree).  Called by the trainers
+    at the start of every train_model and by the importance passes."""
+    if _state["world"] <= 1:
+        return
+    for name in ("theta", "omega", "theta_star", "momentum", "w"):
+        t = getattr(engine, name, None)
+        present = torch.tensor([0 if t is None else 1])
+        if _state["backend"] == "nccl":
+            present = present.cuda()
+        import torch.distributed as td
+        td.all_reduce(present, op=td.ReduceOp.MIN)
+        if int(present.item()) == 1:                       # a buffer that some rank lacks cannot be diverged state
+            broadcast_flat(t)
+
+
+def shared_seed():
+    """One seed for all ranks (drawn by rank 0 from its host generator): the trainers re-seed the host generator with it
+    at the start of every epoch, so that DataLoader shuffles and host-drawn dropout masks agree across ranks."""
+    import torch.distributed as td
+    dev = "cuda" if _state["backend"] == "nccl" else "cpu"
+    t = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).to(dev)
+    td.broadcast(t, src=0)
+    return int(t.item())
+
+
 def allreduce_scalars(vals):
     """Sum python numbers over ranks (epoch statistics: running loss / corrects)."""
     if _state["world"] <= 1:

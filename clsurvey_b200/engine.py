@@ -113,6 +113,15 @@ class Engine:
             self._grad_alt = None
             self.omega = self.theta_star = self.momentum = self.w = None
             self.momentum_valid = False
+        # parameters that LEAVE the model (a head swapped out by utils.replace_last_classifier_layer, or kept by the caller
+        # for evaluation: get_prev_heads, utils.py:235-262) must stop aliasing their old slot of the flat buffers: the slot
+        # is about to be overwritten by their successor, and a later re-bind compares data_ptrs to decide about copying
+        new_ids = {id(p) for p in params}
+        with torch.no_grad():
+            for p_old in getattr(self, "params", None) or []:
+                if id(p_old) not in new_ids:
+                    p_old.data = p_old.data.clone()
+                    p_old.grad = None
         for k in [k for k, e in list(_ENGINES.items()) if e is self]:
             del _ENGINES[k]
         object.__setattr__(model, "_clb_engine", self)
@@ -128,6 +137,17 @@ class Engine:
                 p.grad = self.grad[o:o + p.numel()].view(p.shape)
                 _ENGINES[id(p)] = self
         del old_theta
+        # the plan (ops, activation buffers, workspaces) and captured graphs only depend on the layer structure and on the
+        # flat-buffer addresses: a re-bind that changes neither (get_output_def calls get_engine for every batch; a head
+        # swapped for one of the same shape) keeps them
+        sig = (tuple(self.shapes), tuple(type(m).__name__ for m in model.features.children()),
+               tuple(type(m).__name__ for m in model.classifier.children()), type(getattr(model, "avgpool", None)).__name__)
+        if same_layout and getattr(self, "_sig", None) == sig and getattr(self, "ops", None):
+            for op in self.ops:                       # Dropout ops look at their module's p
+                if op["kind"] == "dropout":
+                    op["module"] = list(model.classifier.children())[op["cls_idx"]]
+            return
+        self._sig = sig
         self._graphs = {}
         self._dp_cut_cache = None                     # offsets may have moved (head swap)
         self._compile()

@@ -58,6 +58,8 @@ class _EngineSGD(optim.SGD):
                     eng.view(eng.momentum, i).copy_(st["momentum_buffer"])
                     loaded = True
         self.first_step = not loaded
+        if loaded:                               # state entries become views of the live engine buffer again, so that a later
+            self._publish_momentum()             # state_dict() (second resume) saves the current momentum, not this snapshot
 
     def _plain_or_penalised(self, n_pen, two_lambda):
         eng = self.engine

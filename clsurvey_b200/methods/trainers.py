@@ -72,6 +72,8 @@ def run_train_model(flavour, model, criterion, optimizer, lr, dset_loaders, dset
     LAST_RUN.clear()
     LAST_RUN.update(log)
     world, rk = cdist.world_size(), cdist.rank()
+    if world > 1:
+        cdist.sync_replicas(eng)                     # replicas start bit-identical (fresh heads are host-drawn per rank)
     epoch_acc = 0.0
     # whole-step CUDA graphs (fwd + loss + bwd + gradient all-reduces + fused update = one graph launch).  Off for
     # models with active Dropout (host-drawn masks change every step).
@@ -80,6 +82,8 @@ def run_train_model(flavour, model, criterion, optimizer, lr, dset_loaders, dset
     seen = set()
     for epoch in range(start_epoch, num_epochs + 1 if si else num_epochs):
         print("Epoch {}/{}".format(epoch, num_epochs - 1))
+        if world > 1:
+            torch.manual_seed(cdist.shared_seed())   # same DataLoader shuffle / dropout draws on every rank
         for phase in ["train", "val"]:
             if phase == "train":
                 optimizer, lr, continue_training = set_lr(optimizer, lr, count=val_beat_counts, stop_ge=si)
@@ -122,13 +126,21 @@ def run_train_model(flavour, model, criterion, optimizer, lr, dset_loaders, dset
                     corr_log[i:i + 1].copy_(eng.correct_dev)
                 elif hi > lo:
                     if phase == "train":
-                        eng.fwd_loss_bwd(x, y, LOSS_MEAN_CE, denom=B, train=True, dp_overlap=True)
+                        masks = None
+                        if has_dropout and world > 1:         # draw for the GLOBAL batch, keep this rank's rows: every rank
+                            masks = {op["cls_idx"]: eng.draw_dropout_mask(op, B)[lo:hi]       # consumes the same RNG stream
+                                     for op in eng.ops if op["kind"] == "dropout"}
+                        eng.fwd_loss_bwd(x, y, LOSS_MEAN_CE, denom=B, train=True, dp_overlap=True, masks=masks)
                     else:
                         eng.forward(x, train=False)
                         eng.loss_head(y, LOSS_MEAN_CE, denom=B, want_grad=False)
                     loss_log[i:i + 1].copy_(eng.loss_dev)
                     corr_log[i:i + 1].copy_(eng.correct_dev)
                 elif phase == "train":
+                    if has_dropout and world > 1:
+                        for op in eng.ops:
+                            if op["kind"] == "dropout":
+                                eng.draw_dropout_mask(op, B)      # keep the host generator in step with the other ranks
                     eng.backward_skip(dp_overlap=True)
                 if phase == "train" and not graphed:
                     if flavour == "sgd":

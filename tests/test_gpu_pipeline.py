@@ -141,3 +141,30 @@ def test_evaluation_forward_path(tmp_path):
     with torch.no_grad():
         acc_ref = 100.0 * (ref(x).argmax(1) == y).float().mean().item()
     assert abs(acc - acc_ref) < 1e-9, (acc, acc_ref)
+
+
+def test_two_heads_round_trip_do_not_alias():
+    """Heads of the same shape swapped in and out of one model (get_prev_heads / test_model, utils.py:235-262,
+    inference.py:56-87): a head that leaves the model must keep its own values, and coming back must restore its logits."""
+    from clsurvey_b200.engine import get_engine
+    torch.manual_seed(3)
+    m = tiny_model()
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(BS, 3, 16, 16, generator=g).cuda()
+    head_a = m.classifier._modules["4"]
+    head_b = nn.Linear(32, NCLS)
+    wb = head_b.weight.detach().clone()
+    eng = get_engine(m, (3, 16, 16), BS)
+    wa = head_a.weight.detach().clone().cpu()
+    logits_a = eng.forward(x).clone()
+    m.classifier._modules["4"] = head_b
+    eng = get_engine(m)
+    logits_b = eng.forward(x).clone()
+    assert not torch.equal(logits_a, logits_b)
+    assert torch.equal(head_a.weight.detach().cpu(), wa), "the head that left the model was overwritten"
+    m.classifier._modules["4"] = head_a
+    eng = get_engine(m)
+    assert torch.equal(eng.forward(x), logits_a)
+    assert torch.equal(head_b.weight.detach().cpu(), wb)
+    m.classifier._modules["4"] = head_b
+    assert torch.equal(get_engine(m).forward(x), logits_b)

@@ -27,6 +27,16 @@ import torch  # noqa: E402
 GLOBAL_BATCH = 200
 IN_SHAPE = (3, 64, 64)
 NUM_CLASSES = 20
+NB = 16                         # distinct synthetic batches the timed steps rotate over
+
+
+def workload_config(model_name):
+    """`config` of the JSON line -- byte-identical in the GPU arm and in `--impl reference` (the driver compares them)."""
+    return {"workload": "%s bs=%d MAS penalised-SGD training step (train_MAS.train_model loop body), 64x64 synthetic inputs, "
+                        "BASELINE configs[2]" % (model_name, GLOBAL_BATCH),
+            "global_batch": GLOBAL_BATCH,
+            "l2": "per-step working set (activations + gradients, ~0.5 GB at batch 200) exceeds the 126 MB L2; inputs rotate "
+                  "over %d distinct batches" % NB}
 
 
 def peaks():
@@ -109,8 +119,9 @@ def synth_batches(n_batches, per, seed):
 
 # ------------------------------------------------------------------------------------------------- CPU arms
 def cpu_reference_steps(model_name, steps, warmup, batch=GLOBAL_BATCH):
-    """The reference's CPU path for this step: oracle/restate.py (the port; /root/reference is absent on the box),
-    all host threads.  Returns (images/sec, cores, sample description)."""
+    """The reference's CPU path for this step: oracle/restate.py (the port; /root/reference is absent on the box) on the
+    host cores.  torch's CPU convolutions do not scale to every thread count, so one step is timed at a few thread counts
+    (all cores, then halvings) and the fastest is used.  Returns (images/sec, threads used, sample text, ms/step)."""
     from oracle import restate
     model = build_model(model_name)
     g = torch.Generator().manual_seed(11)
@@ -118,9 +129,7 @@ def cpu_reference_steps(model_name, steps, warmup, batch=GLOBAL_BATCH):
     reg[-1] = reg[-2] = None
     tr = restate.Trainer(model, "penalty", 0.01, reg=reg, lam=3.0)
     model.train()
-    xs, ys = synth_batches(2, batch, 5)
-    # "all the host threads it can use": torch's CPU conv does not scale to every thread count, so time one step at a
-    # few thread counts (all cores, then halvings) and keep the fastest for the measured sample
+    xs, ys = synth_batches(min(NB, 4), batch, 5)
     ncpu = os.cpu_count() or 1
     best_t, best_n = None, ncpu
     for n in sorted({ncpu, max(ncpu // 2, 1), max(ncpu // 4, 1), min(ncpu, 32), min(ncpu, 16)}, reverse=True):
@@ -133,40 +142,81 @@ def cpu_reference_steps(model_name, steps, warmup, batch=GLOBAL_BATCH):
             best_t, best_n = dt, n
     torch.set_num_threads(best_n)
     for i in range(warmup):
-        tr.step(xs[i % 2], ys[i % 2])
+        tr.step(xs[i % len(xs)], ys[i % len(xs)])
     t0 = time.perf_counter()
     for i in range(steps):
-        tr.step(xs[i % 2], ys[i % 2])
+        tr.step(xs[i % len(xs)], ys[i % len(xs)])
     dt = time.perf_counter() - t0
-    return batch * steps / dt, torch.get_num_threads(), "%d steps of batch %d (%s, penalised SGD) after %d warm-up" % (
-        steps, batch, model_name, warmup), dt / steps * 1e3
+    sample = "%d steps of batch %d after %d warm-up (%s, penalised SGD, %d of %d host threads: fastest of a thread-count sweep)" % (
+        steps, batch, warmup, model_name, best_n, ncpu)
+    return batch * steps / dt, best_n, sample, dt / steps * 1e3
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 8))          # bounded sample: one step is ~1-2 s of CPU work
-    warm = max(1, min(args.warmup, 2))
+    # one CPU step is ~0.5 s: the full --steps / --warmup run stays within minutes up to a few hundred steps
+    steps, warm = max(1, min(args.steps, 400)), max(0, min(args.warmup, 50))
     v, cores, sample, ms = cpu_reference_steps(args.model, steps, warm)
     line = {"impl": "reference", "metric": "images/sec/task", "value": v, "unit": "images/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s bs=%d MAS-style penalised SGD step, 64x64 inputs" % (args.model, GLOBAL_BATCH),
-                       "global_batch": GLOBAL_BATCH, "note": "reference CPU path = oracle/restate.py port on torch CPU"},
-            "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.model),
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "host_cores": os.cpu_count(), "kind": "port",
+                             "sample": sample},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0,
+            "note": "reference CPU path = oracle/restate.py (pinned to the unmodified reference by tests/test_oracle_golden.py) "
+                    "on torch CPU; /root/reference does not exist on the GPU box"}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
+def measured_traffic():
+    """DRAM bytes per step of the conv launches from the committed `ncu --set full` capture (profiles/r2_conv_traffic.json,
+    written by tools/ncu_traffic.py from the same command)."""
+    p = os.path.join(ROOT, "profiles", "r2_conv_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p))
+    return None
+
+
+def conv_roofline(eng, model, step_fn, steps, per, pk, mode_name, ms_graph=None):
+    """Time every conv-stack call of `steps` eager steps with CUDA events on the launching stream (Engine._timed)."""
+    conv_f, _ = conv_flops_per_image(model)
+    eng.conv_events = []
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step_fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_eager = e0.elapsed_time(e1) / steps
+    conv_ms = sum(a.elapsed_time(b) for a, b in eng.conv_events) / steps
+    n_calls = len(eng.conv_events) // steps
+    eng.conv_events = None
+    tf = conv_f * per / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    return {"bound": "tensor", "achieved": tf, "peak": pk["tensor_burst"], "unit": "TFLOP/s", "frac": tf / pk["tensor_burst"],
+            "traffic": None,
+            "kernel": "conv stack: fused first layer + pl::conv_planes_kernel fwd / dgrad / wgrad (+ split-K reduce, bias grad) -- "
+                      "%d calls per step, %s" % (n_calls, mode_name),
+            "algorithmic_gflop_per_step": conv_f * per / 1e9, "ms_per_step_in_kernel": conv_ms, "mma_passes": 3,
+            "frac_of_sustained_peak": tf / pk["tensor"], "frac_of_split_ceiling": 3 * tf / pk["tensor_burst"],
+            "share_of_step": conv_ms / ms_eager,
+            "measured": "CUDA events around every conv-stack call over %d eager steps (%.3f ms/step eager%s)" % (
+                steps, ms_eager, "" if ms_graph is None else ", %.3f ms/step as replayed graph" % ms_graph),
+            "peak_source": pk["src"] + ", bf16 dense burst (the timed region is ~60 ms at full clocks)"}, ms_eager
+
+
 def run_gpu_arm(args):
     # native libraries (NCCL prints its version banner) write to fd 1: keep the real stdout for the ONE JSON line
     real_stdout = os.dup(1)
     os.dup2(2, 1)
     from clsurvey_b200 import _capi, dist as cdist
+    from clsurvey_b200.data import PinnedLoader
     from clsurvey_b200.engine import Engine
+    from clsurvey_b200.methods.MAS import train_MAS
     from clsurvey_b200.methods.optim import Weight_Regularized_SGD
     _capi.lib()
     cdist.init()
@@ -186,13 +236,9 @@ def run_gpu_arm(args):
     model.reg_params["lambda"] = 3.0
     opt = Weight_Regularized_SGD(model.parameters(), 0.01, momentum=0.9, weight_decay=0.0)
     model.train()
-    NB = 16
     xs, ys = synth_batches(NB, GLOBAL_BATCH, 5)
-    xs_h = [x[lo:hi].contiguous().pin_memory() for x in xs]
-    ys_h = [y[lo:hi].contiguous().pin_memory() for y in ys]
-    xs_d = [x.to(dev) for x in xs_h]
-    ys_d = [y.to(dev) for y in ys_h]
-    conv_f, lin_f = conv_flops_per_image(model)
+    xs_d = [x[lo:hi].contiguous().to(dev) for x in xs]
+    ys_d = [y[lo:hi].contiguous().to(dev) for y in ys]
     pk = peaks()
 
     def body(xb, yb):
@@ -211,18 +257,6 @@ def run_gpu_arm(args):
         if state["run"] is None:
             return step_eager(i)
         state["run"](xs_d[i % NB], ys_d[i % NB])         # device->device copy into the graph's static buffers + replay
-
-    xbuf = torch.empty_like(xs_d[0])
-    ybuf = torch.empty_like(ys_d[0])
-
-    def step_e2e(i):                                     # `e2e`: host buffers, H2D + D2H inside the timed region
-        if state["run"] is None:
-            xbuf.copy_(xs_h[i % NB], non_blocking=True)
-            ybuf.copy_(ys_h[i % NB], non_blocking=True)
-            body(xbuf, ybuf)
-        else:
-            state["run"](xs_h[i % NB], ys_h[i % NB])     # pinned host -> static device buffers (H2D) + graph replay
-        return eng.loss_dev.item()                       # D2H read of the step's loss (a host sync, like the reference)
 
     def barrier():
         torch.cuda.synchronize()
@@ -270,23 +304,89 @@ def run_gpu_arm(args):
     if sampler:
         sampler.start()
     ms = timed(step_dev, args.steps)
-    # per-kernel timing of the dominant (conv implicit-GEMM) launches: the same K steps run eagerly with CUDA events
-    # around every conv launch (events cannot be read back from inside a replayed graph)
-    l0 = _capi.lib().clb_launch_count()
-    eng.conv_events = []
-    ms_eager = timed(step_eager, args.steps)
-    launches = (_capi.lib().clb_launch_count() - l0) // max(args.steps, 1) * args.steps
-    conv_ms = sum(a.elapsed_time(b) for a, b in eng.conv_events) / max(args.steps, 1)
-    n_conv_launch = len(eng.conv_events) // max(args.steps, 1)
-    eng.conv_events = None
     value = GLOBAL_BATCH * args.steps / (ms / 1e3)
+    mode_name = {0: "fp32 FFMA (SIMT)", 1: "tf32x3 tcgen05", 2: "tf32x1 tcgen05",
+                 3: "bf16x3 tcgen05: TMA-fed NHWC hi/lo planes (conv) + tf32x3 (linear)"}[args.mm_mode]
+    # per-kernel timing of the dominant (conv) launches: the same K steps run eagerly with CUDA events around every conv
+    # call (events cannot be read back from inside a replayed graph)
+    l0 = _capi.lib().clb_launch_count()
+    roof, ms_eager = conv_roofline(eng, model, step_eager, args.steps, per, pk, mode_name, ms / args.steps)
+    launches = (_capi.lib().clb_launch_count() - l0) // max(args.steps, 1) * args.steps
+    tr = measured_traffic()
+    if tr is not None and world == 1 and GLOBAL_BATCH == 200:
+        roof["traffic"] = tr["bytes_per_step"]
+        roof["traffic_note"] = tr["note"]
+        roof["algorithmic_bytes_per_step"] = tr.get("algorithmic_bytes_per_step")
     # the sampler ran across the two back-to-back device-timed regions (graph replay, per-kernel eager pass): all under
     # load; it is stopped before the end-to-end region so that its nvidia-smi subprocesses never compete with host code
     clocks = sampler.stop() if sampler else None
-    for i in range(min(args.warmup, 3)):
-        step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps)
-    e2e = GLOBAL_BATCH * args.steps / (ms_e2e / 1e3)
+
+    # ---- end to end: the reference-facing plugin call train_MAS.train_model (src/methods/MAS/train_MAS.py:208-335) on an
+    # in-memory task in PINNED HOST memory: every step copies its mini-batch host -> device, the per-batch loss / #correct
+    # are read back once per phase like the trainer does.  One epoch = n_e2e training batches + one validation batch; E2E_EPOCHS
+    # epochs, so that the checkpoint files of the call (epoch.pth.tar at epoch 0, best_model.pth.tar per validation
+    # improvement, train_MAS.py:207-227; 126 MB each) weigh as they do in a task-length run.
+    n_e2e, E2E_EPOCHS = max(args.steps, 40), 10
+    g2 = torch.Generator().manual_seed(6)
+    xe = torch.randn(n_e2e * GLOBAL_BATCH, *IN_SHAPE, generator=g2)
+    ye = torch.randint(0, NUM_CLASSES, (n_e2e * GLOBAL_BATCH,), generator=g2)
+    train_ds = torch.utils.data.TensorDataset(xe, ye)
+    val_ds = torch.utils.data.TensorDataset(xe[:GLOBAL_BATCH].clone(), ye[:GLOBAL_BATCH].clone())
+    warm_ds = torch.utils.data.TensorDataset(xe[:4 * GLOBAL_BATCH].clone(), ye[:4 * GLOBAL_BATCH].clone())
+    import tempfile
+    tmp = tempfile.mkdtemp(prefix="clb_bench_")
+    crit = torch.nn.CrossEntropyLoss()
+
+    def plugin_call(ds, epochs=1):
+        loaders = {"train": PinnedLoader(ds, GLOBAL_BATCH), "val": PinnedLoader(val_ds, GLOBAL_BATCH)}
+        sizes = {"train": len(ds), "val": len(val_ds)}
+        o = train_MAS.Weight_Regularized_SGD(model.parameters(), 0.01, momentum=0.9, weight_decay=0.0)
+        with open(os.devnull, "w") as dn:
+            old = sys.stdout
+            sys.stdout = dn
+            try:
+                train_MAS.train_model(model, crit, o, 0.01, loaders, sizes, True, epochs, exp_dir=tmp + "/", resume="")
+            finally:
+                sys.stdout = old
+
+    plugin_call(warm_ds)                                 # warm-up: graph capture for this configuration, pinned allocations
+    plugin_call(warm_ds)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    plugin_call(train_ds, E2E_EPOCHS)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        import torch.distributed as td
+        t = torch.tensor([ms_e2e], device=dev)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        ms_e2e = t.item()
+    n_e2e_steps = n_e2e * E2E_EPOCHS
+    e2e = GLOBAL_BATCH * n_e2e_steps / (ms_e2e / 1e3)
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+
+    # ---- north_star's conv-roofline case: VGG-11 on a [64, 3, 64, 64] input (233.7 GF fwd + bwd)
+    roof64 = None
+    if rank == 0 and world == 1 and not has_dropout:
+        m64 = build_model(args.model)
+        e64 = Engine(m64, IN_SHAPE, 64)
+        m64.reg_params = {p: {"omega": torch.zeros_like(p.data), "init_val": p.data.clone()} for p in list(m64.parameters())[:-2]}
+        m64.reg_params["lambda"] = 3.0
+        o64 = Weight_Regularized_SGD(m64.parameters(), 0.01, momentum=0.9, weight_decay=0.0)
+        m64.train()
+        x64 = [x[:64].contiguous().to(dev) for x in xs]
+        y64 = [y[:64].contiguous().to(dev) for y in ys]
+
+        def step64(i):
+            e64.fwd_loss_bwd(x64[i % NB], y64[i % NB], denom=64, train=True)
+            o64.step(m64.reg_params)
+        for i in range(3):
+            step64(i)
+        roof64, _ = conv_roofline(e64, m64, step64, args.steps, 64, pk, mode_name)
+        del e64, m64, o64
 
     # Fisher / Omega accumulator bandwidth (AlexNet-sized flat buffer, config C2: P = 57,085,780 > L2)
     fisher = None
@@ -307,51 +407,33 @@ def run_gpu_arm(args):
         fms = ev[0].elapsed_time(ev[1]) / reps
         gbs = 12.0 * P / (fms * 1e-3) / 1e9
         fisher = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
-                  "traffic": None, "kernel": "fisher_kernel (omega += g*g/N)", "bytes_per_param": 12, "params": P,
+                  "traffic": 12.0 * P, "traffic_note": "algorithmic = measured: ncu dram bytes 629-630 MB per launch vs 685 MB "
+                  "algorithmic (the tail of omega is still dirty in L2 when the launch retires), profiles/r1_ncu_full_fisher.csv",
+                  "kernel": "fisher_kernel (omega += g*g/N)", "bytes_per_param": 12, "params": P,
                   "ms_per_launch": fms, "peak_source": pk["src"]}
         del om, gr
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores, sample, _ = cpu_reference_steps(args.model, 5, 1)
-        cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
+        cpu = {"value": v, "unit": "images/s", "cores": cores, "host_cores": os.cpu_count(), "kind": "port", "sample": sample}
 
     if rank == 0:
-        conv_tf = conv_f * per / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-        mode_name = {0: "fp32 FFMA (SIMT)", 1: "tf32x3 tcgen05", 2: "tf32x1 tcgen05",
-                     3: "bf16x3 tcgen05 (conv fwd/dgrad/wgrad) + tf32x3 (rest)"}[args.mm_mode]
         line = {
             "metric": "images/sec/task", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": {0: "f32", 1: "tf32x3->f32", 2: "tf32", 3: "bf16x3/tf32x3->f32"}[args.mm_mode],
-            "data": "synthetic",
-            "config": {"workload": "%s bs=%d MAS-style penalised SGD step, 64x64 inputs (BASELINE configs[2])" % (
-                args.model, GLOBAL_BATCH), "global_batch": GLOBAL_BATCH, "per_gpu_batch": per,
-                "parallelism": "dp%d" % world, "matmul_mode": mode_name,
-                "launch": "cuda graph replay (1 graph launch = %d kernels)" % (launches // max(args.steps, 1)) if state["run"] else "eager",
-                "l2": "per-step working set (activations+grads ~0.6 GB at batch 200) exceeds the 126 MB L2; inputs "
-                      "rotate over %d distinct batches" % NB},
+            "data": "synthetic", "config": workload_config(args.model),
+            "details": {"per_gpu_batch": per, "parallelism": "dp%d" % world, "matmul_mode": mode_name,
+                        "launch": "cuda graph replay (1 graph launch = %d kernels)" % (launches // max(args.steps, 1)) if state["run"] else "eager"},
             "clocks": clocks,
-            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(xbuf.numel() * 4 + ybuf.numel() * 8),
-                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(per * (IN_SHAPE[0] * IN_SHAPE[1] * IN_SHAPE[2] * 4 + 8)),
+                    "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / n_e2e_steps, "steps": n_e2e_steps,
+                    "api": "train_MAS.train_model(model, criterion, Weight_Regularized_SGD, lr, loaders, sizes, True, %d epochs, ...) on "
+                           "a pinned-host in-memory task: %d training batches + 1 validation batch per epoch, per-phase loss read-back, "
+                           "epoch.pth.tar + best_model.pth.tar checkpoints written (background writer)" % (E2E_EPOCHS, n_e2e)},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "achieved": conv_tf, "peak": pk["tensor"], "unit": "TFLOP/s",
-                         "frac": conv_tf / pk["tensor"], "traffic": None,
-                         "kernel": "conv2d implicit-GEMM fwd+wgrad+dgrad (%d launches/step, %s)" % (n_conv_launch, mode_name),
-                         "algorithmic_gflop_per_step": conv_f * per / 1e9, "ms_per_step_in_kernel": conv_ms,
-                         # the fp32-parity split issues 3 MMAs per algorithmic one (bf16 rate in mode 3, tf32 = half of
-                         # it in mode 1): fraction of the rate the tensor pipe can give to THIS arithmetic
-                         "mma_passes": {0: 0, 1: 3, 2: 1, 3: 3}[args.mm_mode],
-                         "frac_of_split_ceiling": (conv_tf * {0: 0, 1: 6, 2: 2, 3: 3}[args.mm_mode] / pk["tensor"]),
-                         "share_of_step": conv_ms / (ms_eager / args.steps),
-                         "measured": "CUDA events around every conv launch over %d eager steps (%.3f ms/step eager, "
-                                     "%.3f ms/step as replayed graph)" % (args.steps, ms_eager / args.steps, ms / args.steps),
-                         "peak_source": pk["src"] + ", bf16 dense sustained",
-                         "traffic_note": "aggregate of all conv launches, so no single per-launch figure; ncu --set full "
-                                         "per launch: 16-106 MB DRAM read + 0-59 MB written = the operand / output bytes "
-                                         "(operands are L2-resident, no re-reads): profiles/r1_ncu_full_bf16*.csv"},
-            "roofline_fisher": fisher,
-            "cpu_baseline": cpu,
+            "roofline": roof, "roofline_n64": roof64, "roofline_fisher": fisher, "cpu_baseline": cpu,
         }
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     # NCCL keeps a communicator alive while a captured graph still references it: drop the graphs first, and never let

@@ -22,6 +22,7 @@ SIGNATURES = {
     "clb_set_matmul_mode": [c_i],
     "clb_get_matmul_mode": [],
     "clb_launch_count": [],
+    "clb_memset_zero": [c_p, c_sz, c_p],
     "clb_conv2d_fwd": [c_p, c_p, c_p, c_p, c_p] + [c_i] * 10 + [c_p],
     "clb_conv2d_dgrad": [c_p, c_p, c_p, c_p] + [c_i] * 9 + [c_p],
     "clb_conv2d_wgrad_ws": [c_i] * 9,

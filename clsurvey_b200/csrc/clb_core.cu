@@ -59,4 +59,9 @@ int clb_set_matmul_mode(int mode) {
 }
 int clb_get_matmul_mode(void) { return clb::mm_mode(); }
 unsigned long long clb_launch_count(void) { return clb::launches(); }
+int clb_memset_zero(void* p, size_t bytes, void* stream) {
+    CLB_CHECK_ARG(p != nullptr || bytes == 0);
+    if (bytes) CLB_CUDA(cudaMemsetAsync(p, 0, bytes, clb::as_stream(stream)));
+    return CLB_OK;
+}
 }

@@ -273,6 +273,17 @@ class Engine:
         for op in ops:
             if op["kind"] == "linear":
                 ws_bytes = max(ws_bytes, _capi.lib().clb_linear_ws(B, op["inf"], op["outf"]))
+        # importance passes (EWC Fisher / MAS omega) fuse `omega (+)= f(dW)` into the split-K reduction of the planes convs
+        # (clb_planes_conv_wgrad, imp_mode); the flat-buffer ranges NOT covered by those weights get the streaming kernel
+        covered = sorted((self.offsets[op["w"]], self.offsets[op["w"]] + (self.numels[op["w"]] + 3) // 4 * 4)
+                         for op in ops if op["kind"] == "conv" and op.get("planes"))
+        self._imp_rest, pos = [], 0
+        for a, b in covered:
+            if a > pos:
+                self._imp_rest.append((pos, a - pos))
+            pos = b
+        if pos < self.total:
+            self._imp_rest.append((pos, self.total - pos))
         self._wbatch = None
         pconvs = [op for op in ops if op["kind"] == "conv" and op.get("planes")]
         if pconvs:
@@ -445,8 +456,8 @@ class Engine:
         n = self._n
         ncols = self.n_outputs - col_off if ncols is None else ncols
         denom = float(n if denom is None else denom)
-        self.loss_dev.zero_()
-        self.correct_dev.zero_()
+        call("clb_memset_zero", _ptr(self.loss_dev), 4, _stream())
+        call("clb_memset_zero", _ptr(self.correct_dev), 4, _stream())
         if labels is not None:
             labels = labels.to(self.device, torch.int64).contiguous()
         self._labels = labels
@@ -469,13 +480,21 @@ class Engine:
             self._dp_cut_cache = cut
         return self._dp_cut_cache
 
-    def backward(self, accumulate=False, dp_overlap=False):
-        """dlogits -> parameter gradients (flat self.grad).  accumulate=True adds to the existing gradient
+    def backward(self, accumulate=False, dp_overlap=False, importance=None):
+        """dlogits -> parameter gradients (flat self.grad).  importance = (1, data_len) [EWC: omega += g*g/data_len,
+        main_EWC.py:151-156] or (2, prev_size, curr_size) [MAS: omega = (omega*prev + |g|)/curr, train_MAS.py:163-177]
+        applies that update to self.omega as part of this backward pass: inside the split-K reduction of the planes convs
+        (which holds every final dW element in a register anyway), one streaming launch per remaining range.  accumulate=True adds to the existing gradient
         (GEM memory mini-batches, gem.py:239-256, never zero the grads in between).  dp_overlap=True (data-parallel
         training steps only): the caller promises to call dist.allreduce_grads(self) next; the tail of the flat
         gradient is then all-reduced on a side stream as soon as its last layer is done."""
         n, s = self._n, _stream()
         self._dp_pending = None
+        imp_mode, imp_a, imp_b = 0, 0.0, 0.0
+        if importance is not None:
+            assert not accumulate and self.omega is not None
+            imp_mode, imp_a = int(importance[0]), float(importance[1])
+            imp_b = float(importance[2]) if len(importance) > 2 else 0.0
         cut_op, cut_off = (0, 0)
         if dp_overlap and not accumulate:
             from . import dist as _dist
@@ -546,7 +565,8 @@ class Engine:
                 x_pl = op["inp"]                                      # planes of this conv's (post-ReLU) input
                 self._timed(call, "clb_planes_conv_wgrad", _ptr(x_pl[0]), _ptr(x_pl[1]), _ptr(d[0]), _ptr(d[1]),
                             _ptr(self.view(gdst, op["w"])), _ptr(self.view(gdst, op["b"])), _ptr(self.ws), self.ws.numel() * 4,
-                            n, op["H"], op["W"], op["C"], op["K"], 0, 0, 0.0, 0.0, s)
+                            n, op["H"], op["W"], op["C"], op["K"], imp_mode,
+                            _ptr(self.view(self.omega, op["w"])) if imp_mode else 0, imp_a, imp_b, s)
                 prev = self.ops[i - 1]
                 nxt = self.dpl[pl_other]
                 mask = 0
@@ -582,14 +602,21 @@ class Engine:
                 self.n_launch += 4
         if accumulate:
             call("clb_axpby", _ptr(self.grad), _ptr(self.grad), _ptr(gdst), 1.0, self.total, s)
+        if imp_mode:
+            for off, cnt in self._imp_rest:
+                if imp_mode == 1:
+                    call("clb_fisher_accum", _ptr(self.omega[off:]), _ptr(self.grad[off:]), imp_a, cnt, s)
+                else:
+                    call("clb_mas_accum", _ptr(self.omega[off:]), _ptr(self.grad[off:]), imp_a, imp_b, cnt, s)
+                self.n_launch += 1
 
     def zero_grad(self):
-        self.grad.zero_()
+        call("clb_memset_zero", _ptr(self.grad), self.grad.numel() * 4, _stream())
 
     def backward_skip(self, dp_overlap=False):
         """A rank whose shard of the mini-batch is empty contributes a zero gradient -- through the same sequence of
         collectives as the ranks that ran backward(dp_overlap=...)."""
-        self.grad.zero_()
+        self.zero_grad()
         self._dp_pending = None
         if dp_overlap:
             from . import dist as _dist
@@ -600,10 +627,10 @@ class Engine:
 
     # ------------------------------------------------------------------ composite steps
     def fwd_loss_bwd(self, x, y, mode=LOSS_MEAN_CE, denom=None, train=True, masks=None, col_off=0, ncols=None,
-                     accumulate=False, dp_overlap=False):
+                     accumulate=False, dp_overlap=False, importance=None):
         self.forward(x, train=train, masks=masks)
         self.loss_head(y, mode, denom, col_off, ncols, want_grad=True)
-        self.backward(accumulate=accumulate, dp_overlap=dp_overlap)
+        self.backward(accumulate=accumulate, dp_overlap=dp_overlap, importance=importance)
 
     def fwd_loss(self, x, y, mode=LOSS_MEAN_CE, col_off=0, ncols=None):
         self.forward(x, train=False)

@@ -50,7 +50,7 @@ def _importance_loader(data_dir, reg_sets, batch_size, split="train"):
     for data_path in reg_sets:                      # like the reference only the LAST loader is used (main_EWC.py:93-117)
         dset = torch.load(data_path, weights_only=False) if isinstance(data_path, str) else data_path
         dset = dset[split]
-    loader = torch.utils.data.DataLoader(dset, batch_size=batch_size, shuffle=False, num_workers=0)
+    loader = common.make_loader(dset, batch_size, shuffle=False)
     return dset, loader
 
 
@@ -76,9 +76,8 @@ def diag_fisher(model, dset_loader, data_len):
         if b % world != rk:
             continue
         x = x if x.is_cuda else x.to(eng.device, non_blocking=True)
-        eng.fwd_loss_bwd(x, label, LOSS_SUM_NLL, train=False)
-        call("clb_fisher_accum", _ptr(eng.omega), _ptr(eng.grad), float(data_len), eng.total, _stream())
-        eng.n_launch += 1
+        # omega += g*g / data_len fused into this batch's backward pass (Engine.backward, importance=...)
+        eng.fwd_loss_bwd(x, label, LOSS_SUM_NLL, train=False, importance=(1, float(data_len)))
     cdist.allreduce_flat(eng.omega)
     _zero_unregistered(eng, reg_params)
     return model

@@ -23,8 +23,7 @@ def compute_importance_l2(model, optimizer, lr_scheduler, dset_loaders, use_gpu)
 
     Data parallel: whole batches are dealt round-robin; each rank accumulates sum_b |g_b| (prev=1, curr=1 form) and the
     all-reduced sum is divided once -- equal to the reference's running mean for equal batch sizes.
-    (The recurrence unrolls to omega = mean_b(|g_b| / n_b), so ragged batches could be sharded too by accumulating
-    |g_b| / n_b per batch; the sharded path currently insists on equal batch sizes -- the BASELINE configs have them.)"""
+    The recurrence unrolls to omega = mean_b(|g_b| / n_b), so ragged batches shard too."""
     eng = engine_of(model.parameters())
     model.eval()
     world, rk = cdist.world_size(), cdist.rank()
@@ -33,25 +32,27 @@ def compute_importance_l2(model, optimizer, lr_scheduler, dset_loaders, use_gpu)
         for dset_loader in dset_loaders:
             for inputs, labels in dset_loader:
                 x = inputs if inputs.is_cuda else inputs.to(eng.device, non_blocking=True)
-                eng.fwd_loss_bwd(x, None, LOSS_SUM_SQ, train=False)
-                optimizer.step(model.reg_params, index, labels.size(0))
+                # Objective_After_SGD.step (train_MAS.py:163-177) fused into this batch's backward pass
+                sync_reg_params(eng, model.reg_params, need_w=False)
+                n_b = labels.size(0)
+                eng.fwd_loss_bwd(x, None, LOSS_SUM_SQ, train=False, importance=(2, float(index * n_b), float((index + 1) * n_b)))
                 index += 1
     else:
         from ..._capi import call
         from ...engine import _ptr, _stream
         sync_reg_params(eng, model.reg_params, need_w=False)
-        n_b = None
+        # the recurrence unrolls to omega = (1 / n_batches) * sum_b |g_b| / n_b with n_b the size of batch b -- also for
+        # ragged last batches: each rank adds |g_b| / n_b for its batches ((omega*n_b + |g|) / n_b), the sums are all-reduced
+        # and divided by the number of batches once
         for dset_loader in dset_loaders:
             for inputs, labels in dset_loader:
-                n_b = labels.size(0) if n_b is None else n_b
-                assert labels.size(0) == n_b, "sharded MAS pass needs equal batch sizes"
                 if index % world == rk:
                     x = inputs if inputs.is_cuda else inputs.to(eng.device, non_blocking=True)
-                    eng.fwd_loss_bwd(x, None, LOSS_SUM_SQ, train=False)
-                    call("clb_mas_accum", _ptr(eng.omega), _ptr(eng.grad), 1.0, 1.0, eng.total, _stream())
+                    n_b = float(labels.size(0))
+                    eng.fwd_loss_bwd(x, None, LOSS_SUM_SQ, train=False, importance=(2, n_b, n_b))
                 index += 1
         cdist.allreduce_flat(eng.omega)
-        eng.zero_grad()                                   # omega <- (omega*1 + |0|) / (n_batches * n_b)
-        call("clb_mas_accum", _ptr(eng.omega), _ptr(eng.grad), 1.0, float(index * n_b), eng.total, _stream())
+        eng.zero_grad()                                   # omega <- (omega*1 + |0|) / n_batches
+        call("clb_mas_accum", _ptr(eng.omega), _ptr(eng.grad), 1.0, float(max(index, 1)), eng.total, _stream())
     _zero_unregistered(eng, model.reg_params)
     return model

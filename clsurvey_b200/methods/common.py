@@ -16,8 +16,15 @@ def load_model(path):
 
 
 def make_loaders(dsets, batch_size, shuffle=True, workers=0):
-    return {x: torch.utils.data.DataLoader(dsets[x], batch_size=batch_size, shuffle=shuffle, num_workers=workers,
-                                           pin_memory=False) for x in ["train", "val"]}
+    """The reference's per-task loaders (main_EWC.py:29-31: DataLoader, shuffle, 8 workers).  The un-augmented task is cached
+    on the device once (clsurvey_b200/data.py) and served in the SAME order a DataLoader would draw."""
+    from .. import data as cdata
+    return cdata.make_loaders(dsets, batch_size, shuffle)
+
+
+def make_loader(dset, batch_size, shuffle=False):
+    from .. import data as cdata
+    return cdata.make_loaders({"x": dset}, batch_size, shuffle, phases=("x",))["x"]
 
 
 def sample_shape(dset):

@@ -145,8 +145,8 @@ class Finetune(Method):
         assert len(dataset_path) == 1, "dataset concatenation (Joint) is outside the hot path"
         d = dataset_path[0]
         wrapper = torch.load(d, weights_only=False) if isinstance(d, str) else d
-        loaders = {x: torch.utils.data.DataLoader(wrapper[x], batch_size=batch_size, shuffle=True, num_workers=0)
-                   for x in ['train', 'val']}
+        from . import common
+        loaders = common.make_loaders(wrapper, batch_size, shuffle=True)      # device-resident task cache (8f-2)
         sizes = {x: len(wrapper[x]) for x in ['train', 'val']}
         classes = {x: [wrapper[x].classes] for x in ['train', 'val']}
         return loaders, sizes, classes

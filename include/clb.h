@@ -51,6 +51,9 @@ int clb_sm_count(int* out);
 int clb_set_matmul_mode(int mode);
 int clb_get_matmul_mode(void);
 unsigned long long clb_launch_count(void); /* kernels launched by this library so far (process-wide) */
+/* stream-ordered zero fill (cudaMemsetAsync; a memset node under graph capture): the per-step resets of the loss /
+ * #correct accumulators and of the gradient buffer -- optimizer.zero_grad() of train_EWC.py:177 */
+int clb_memset_zero(void* p, size_t bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Layer kernels (a2, a3).  Replace model(inputs) / loss.backward() of train_EWC.py:181-187.

@@ -136,8 +136,34 @@ bl = [(f["data"][0][b*16:(b+1)*16], f["data"][1][b*16:(b+1)*16]) for b in range(
 om = torch.cat([o.reshape(-1) for o in restate.fisher_pass(m4, bl, 64)])
 err2 = (acc - om).abs().max().item() / om.abs().max().item()
 assert err2 < 1e-5, err2
+# MAS omega pass with RAGGED batches (16, 16, 16, 8), sharded by whole batches: the reference's running mean
+# (train_MAS.py:163-177: omega <- (omega*b*n_b + |g|)/((b+1)*n_b) with n_b the CURRENT batch size) unrolls to
+# (1/n_batches) * sum_b |g_b|/n_b, which is what the sharded pass of methods/MAS/train_MAS.py accumulates
+xs, ys = f["data"][0][:56], f["data"][1][:56]
+rag = [(xs[i:i + 16], ys[i:i + 16]) for i in range(0, 56, 16)]
+acc = torch.zeros_like(ref)
+for b in dist.shard_batches(len(rag)):
+    m5 = tiny_model(f["init"]); m5.eval()
+    (m5(rag[b][0]) ** 2).sum().backward()
+    g = torch.cat([p.grad.reshape(-1) for p in m5.parameters()])
+    n_b = float(rag[b][0].shape[0])
+    acc = (acc * n_b + g.abs()) / n_b
+dist.allreduce_flat(acc)
+acc = acc / len(rag)
+om = torch.cat([o.reshape(-1) for o in restate.mas_pass(tiny_model(f["init"]), rag)])
+err3 = (acc - om).abs().max().item() / om.abs().max().item()
+assert err3 < 1e-5, err3
 tot = dist.allreduce_scalars([1.0, float(dist.rank())])
 assert tot == [2.0, 1.0]
+# replicas: one seed for all ranks, rank 0's buffers everywhere
+torch.manual_seed(100 + dist.rank())
+s1 = dist.shared_seed()
+t = torch.tensor([float(s1 %% 1000)])
+dist.allreduce_flat(t)
+assert t.item() == 2.0 * (s1 %% 1000)
+buf = torch.full((8,), float(dist.rank() + 1))
+dist.broadcast_flat(buf)
+assert buf.eq(1.0).all()
 dist.shutdown()
 print("DP_OK", dist.rank() if False else os.environ["RANK"])
 '''

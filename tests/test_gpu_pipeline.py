@@ -121,8 +121,10 @@ def test_cuda_graph_replay_equals_eager(tmp_path, monkeypatch):
 
 
 def test_evaluation_forward_path(tmp_path):
-    """f-1: `test_model` / `get_output_def` (src/framework/inference.py:8-87, method.py:230-235) through the engine:
-    accuracy equals the torch-CPU evaluation of the same model with the same head."""
+    """f-1: `test_model` / `get_output_def` / `inference_eval` / `get_prev_heads` (src/framework/inference.py:8-87,
+    method.py:230-235,1066-1087, utils.py:235-262) through the engine: overall accuracy AND the per-class counters equal
+    the torch-CPU evaluation of the same model with the same head -- for a head passed directly and for a head fetched by
+    path from the model of an earlier task while a later model (different head, same trunk) is evaluated."""
     import copy
     from clsurvey_b200.framework import inference
     from clsurvey_b200.methods import method as M
@@ -133,14 +135,36 @@ def test_evaluation_forward_path(tmp_path):
             if hasattr(m, "weight"):
                 m.weight.mul_(30.0)                      # spread the logits so that arg-max is not degenerate
     ref = copy.deepcopy(model)
-    ds = {"test": _task(77, 96)}
+    ds = {"train": _task(76, 32), "val": _task(78, 32), "test": _task(77, 96)}
     head = copy.deepcopy(model.classifier._modules["4"])
-    acc = inference.test_model(M.EWC(), model, ds, 0, target_head=[head], batch_size=BS, subset="test")
+    acc = inference.test_model(M.EWC(), model, ds, 0, target_head=[head], batch_size=BS, subset="test", per_class_stats=True)
     ref.eval()
     x, y = ds["test"].tensors
     with torch.no_grad():
-        acc_ref = 100.0 * (ref(x).argmax(1) == y).float().mean().item()
-    assert abs(acc - acc_ref) < 1e-9, (acc, acc_ref)
+        pred = ref(x).argmax(1)
+    assert abs(acc - 100.0 * (pred == y).float().mean().item()) < 1e-9
+    correct, total = inference.test_model.last_class_stats
+    for c in range(NCLS):
+        assert total[c] == float((y == c).sum()) and correct[c] == float(((pred == y) & (y == c)).sum())   # exact counters
+    # a later model (new head) evaluated on the old task with the old model's head, both given as paths
+    p1 = str(tmp_path / "task1_model.pth.tar")
+    torch.save(ref, p1)
+    later = copy.deepcopy(ref)
+    torch.manual_seed(9)
+    later.classifier._modules["4"] = nn.Linear(32, NCLS)
+    p2 = str(tmp_path / "task2_model.pth.tar")
+    torch.save({"model": later}, p2)                      # epoch.pth.tar-style dict: both forms load (method.py:1069-1070)
+    dpath = str(tmp_path / "task1_data.pth")
+    torch.save(ds, dpath)
+    args = types.SimpleNamespace(eval_model_path=p2, head_paths=[p1], dset_path=dpath, test_set="test", batch_size=BS,
+                                 eval_dset_idx=0)
+    manager = types.SimpleNamespace(method=M.EWC())
+    acc2 = M.EWC.inference_eval(args, manager)
+    assert abs(acc2 - acc) < 1e-9                         # same trunk + the task-1 head = the task-1 accuracy
+    with torch.no_grad():
+        later.eval()
+        acc_wrong_head = 100.0 * (later(x).argmax(1) == y).float().mean().item()
+    assert abs(acc_wrong_head - acc) > 1e-9               # (the fresh head alone would give something else)
 
 
 def test_two_heads_round_trip_do_not_alias():

@@ -650,7 +650,9 @@ class Engine:
             ys = torch.zeros(n, dtype=torch.int64, device=self.device)
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
-            with torch.cuda.graph(g):
+            # thread_local: the background checkpoint writer (methods/trainers.py) may issue D2H copies from its own thread
+            # while this thread captures
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 body(xs, ys)
             ent = (g, xs, ys)
             self._graphs[key] = ent

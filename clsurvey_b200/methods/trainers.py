@@ -80,6 +80,29 @@ class _CheckpointWriter:
             raise e
 
 
+def set_lr(optimizer, lr, count, stop_ge=False):
+    """Early stop (count > 10; SI: >= 10) / decay x0.1 at count == 5 (train_SGD.py:10-30, train_SI.py:129-141)."""
+    continue_training = True
+    if (count >= 10) if stop_ge else (count > 10):
+        continue_training = False
+        print("training terminated")
+    if count == 5:
+        lr = lr * 0.1
+        print("lr is set to {}".format(lr))
+        for param_group in optimizer.param_groups:
+            param_group["lr"] = lr
+    return optimizer, lr, continue_training
+
+
+def save_cuda_mem_req(out_dir, out_filename="cuda_mem_req.pth.tar"):
+    """Same side file as utils.save_cuda_mem_req (src/utilities/utils.py:85-97)."""
+    out_dir = os.path.dirname(out_dir)
+    if not out_dir or not os.path.isdir(out_dir):
+        return
+    torch.save({"cuda_memory_allocated": torch.cuda.memory_allocated(), "cuda_memory_cached": torch.cuda.memory_reserved()},
+               os.path.join(out_dir, out_filename))
+
+
 class _StagedBatches:
     """Iterate a loader ONE batch ahead: a host batch's rows of this rank are copied host -> device on a side stream into one
     of two staging buffers while the previous step still computes (the reference copies inline, `inputs.cuda()`,

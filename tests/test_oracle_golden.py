@@ -247,3 +247,40 @@ def test_long_run_epoch_protocol_matches_reference():
         assert n_calls == r["n_criterion_calls"], (which, n_calls, r["n_criterion_calls"])
         assert abs(best - r["best_acc"]) < 1e-12, (which, best, r["best_acc"])
     assert g["diverge_ewc"]["n_criterion_calls"] == len(ld["train"]) and g["diverge_sgd"]["n_criterion_calls"] == 4 * per_epoch
+
+
+def test_wide_fixture_matches_reference():
+    """tests/golden/wide.pt (EWC + SI on a 64 / 64 / 128-channel VGGSlim, the layers the tensor-core kernels take): the
+    restatement against the unmodified reference, and the fixture's own claim that no ReLU / pool decision of the run
+    sits within 1e-5 of its boundary (found by a seed search, oracle/gen_golden.py MarginMonitor)."""
+    from tests.util import WIDE_BS, wide_model
+    g = load_golden("wide")
+    assert g["ewc"]["min_margin"] >= 1.5e-5 and g["si"]["min_margin"] >= 1.5e-5
+    r = g["ewc"]
+    m = wide_model(r["init"])
+    names = [n for n, _ in m.named_parameters()]
+    xp, yp = r["prev_data"]
+    om = restate.fisher_pass(m, batches(xp, yp, WIDE_BS), len(xp))
+    for n, o in zip(names, om):
+        assert rel_err(o, r["reg_after_pass"][n]["omega"]) <= TOL, n
+    reg = [dict(omega=o.clone(), init_val=p.data.clone()) for o, p in zip(om, m.parameters())]
+    m.classifier._modules["4"].load_state_dict(r["new_head"])
+    reg[-1] = reg[-2] = None
+    ld, sizes = loaders(r["data"], WIDE_BS)
+    tr = restate.Trainer(m, "penalty", r["lr"], reg=reg, lam=r["lam"], wd=r["wd"])
+    best, _, _ = tr.train_model(ld, sizes, r["epochs"])
+    assert abs(best - r["best_acc"]) < 1e-12
+    for k, v in r["final"].items():
+        assert rel_err(m.state_dict()[k], v) <= TOL, k
+    r = g["si"]
+    m = wide_model(r["init"])
+    reg = [dict(omega=r["reg_before"][n]["omega"].clone(), w=torch.zeros_like(p), init_val=r["reg_before"][n]["init_val"].clone())
+           for n, p in m.named_parameters()]
+    ld, sizes = loaders(r["data"], WIDE_BS)
+    tr = restate.Trainer(m, "si", r["lr"], reg=reg, lam=r["lam"])
+    best, _, _ = tr.train_model(ld, sizes, r["epochs"])
+    assert abs(best - r["best_acc"]) < 1e-12
+    for k, v in r["final"].items():
+        assert rel_err(m.state_dict()[k], v) <= TOL, k
+    for n, rg in zip(names, reg):
+        assert rel_err(rg["w"], r["reg_after"][n]["w"]) <= 1e-3, n

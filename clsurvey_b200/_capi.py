@@ -58,6 +58,7 @@ SIGNATURES = {
     "clb_fisher_accum": [c_p, c_p, c_f, c_i64, c_p],
     "clb_mas_accum": [c_p, c_p, c_f, c_f, c_i64, c_p],
     "clb_si_consolidate": [c_p, c_p, c_p, c_p, c_f, c_i64, c_p],
+    "clb_imm_merge_accum": [c_p, c_p, c_p, c_p, c_i64, c_i, c_p],
     "clb_axpby": [c_p, c_p, c_p, c_f, c_i64, c_p],
     "clb_gem_dots_gram": [c_p, c_p, c_i64, c_i64, c_p, c_i, c_p, c_p, c_p],
     "clb_gem_solve_qp": [c_p, c_p, c_i, c_d, c_d, c_p, c_p, c_p],

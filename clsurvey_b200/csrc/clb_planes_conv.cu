@@ -403,14 +403,16 @@ int conv_fwd(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi, c
     return bn_tile == 128 ? launch<0, 128>(a_hi, a_lo, b_hi, b_lo, p, s) : launch<0, 64>(a_hi, a_lo, b_hi, b_lo, p, s);
 }
 
-// split-K plan of the wgrad GEMM [Cout x 9 Cred] over N*H*W pixels; fixed 148-SM target => device-independent summation order
+// split-K plan of the wgrad GEMM [Cout x 9 Cred] over N*H*W pixels: as many splits as fill ONE wave of the 148 SMs (every
+// persistent CTA then does exactly one equally long work item -- no tail round -- and the partial-sum workspace is as small as
+// the parallelism allows: 1 split, i.e. no reduction traffic at all, for the 144-tile layers).  Fixed 148 => the summation
+// order, and with it every bit of dW, does not depend on the device it runs on.
 void wgrad_plan(int N, int H, int W, int Cred, int Cout, int* splits, int* kb_per_split, int* n_kb) {
     const TileGeom g = make_geom(64, H, W);
     const int nkb = ((N + g.bn - 1) / g.bn) * g.tiles_h;
     const int tiles = ((Cout + 127) / 128) * ((9 * (Cred / 64) + 1) / 2);
-    int want = (2 * 148 + tiles - 1) / tiles;
-    const int cap = nkb / 4 > 1 ? nkb / 4 : 1;
-    if (want > cap) want = cap;
+    int want = 148 / tiles;
+    if (want > nkb) want = nkb;
     if (want < 1) want = 1;
     const int per = (nkb + want - 1) / want;
     *kb_per_split = per;

@@ -58,24 +58,32 @@ struct WeightBatch {
     int K[kMax], C[kMax];
 };
 __global__ void __launch_bounds__(256) weights_to_planes_batch_kernel(const __grid_constant__ WeightBatch b) {
+    // thread = two adjacent elements of the contiguous output dimension (c for the forward layout, k for the dgrad layout):
+    // 4-byte stores, coalesced along that dimension; C and K are multiples of 64
     const int layer = blockIdx.y >> 1;
     const bool dgrad = blockIdx.y & 1;
     const int K = b.K[layer], C = b.C[layer];
     const float* __restrict__ w = b.w[layer];
-    uint16_t* __restrict__ o_hi = dgrad ? b.wt_hi[layer] : b.wf_hi[layer];
-    uint16_t* __restrict__ o_lo = dgrad ? b.wt_lo[layer] : b.wf_lo[layer];
-    const int64_t total = (int64_t)K * C, gs = (int64_t)gridDim.x * blockDim.x;
+    uint32_t* __restrict__ o_hi = reinterpret_cast<uint32_t*>(dgrad ? b.wt_hi[layer] : b.wf_hi[layer]);
+    uint32_t* __restrict__ o_lo = reinterpret_cast<uint32_t*>(dgrad ? b.wt_lo[layer] : b.wf_lo[layer]);
+    const int64_t total = (int64_t)K * C / 2, gs = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gs) {
         int k, c;
-        if (!dgrad) { k = (int)(i / C); c = (int)(i - (int64_t)k * C); }
-        else { c = (int)(i / K); k = (int)(i - (int64_t)c * K); }
-        const float* src = w + ((int64_t)k * C + c) * 9;
+        const float *s0, *s1;
+        if (!dgrad) {
+            k = (int)(i / (C / 2)); c = 2 * (int)(i - (int64_t)k * (C / 2));
+            s0 = w + ((int64_t)k * C + c) * 9; s1 = s0 + 9;
+        } else {
+            c = (int)(i / (K / 2)); k = 2 * (int)(i - (int64_t)c * (K / 2));
+            s0 = w + ((int64_t)k * C + c) * 9; s1 = s0 + (int64_t)C * 9;
+        }
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
-            uint32_t hi, lo;
-            split1(__ldg(src + t), hi, lo);
-            const int64_t o = dgrad ? ((int64_t)c * 9 + (8 - t)) * K + k : ((int64_t)k * 9 + t) * C + c;
-            o_hi[o] = (uint16_t)hi; o_lo[o] = (uint16_t)lo;
+            uint32_t h0, l0, h1, l1;
+            split1(__ldg(s0 + t), h0, l0);
+            split1(__ldg(s1 + t), h1, l1);
+            const int64_t o = dgrad ? (((int64_t)c * 9 + (8 - t)) * K + k) >> 1 : (((int64_t)k * 9 + t) * C + c) >> 1;
+            o_hi[o] = h0 | (h1 << 16); o_lo[o] = l0 | (l1 << 16);
         }
     }
 }
@@ -90,7 +98,7 @@ int weights_to_planes_batch(int n, const float* const* w, void* const* wf_hi, vo
         b.K[i] = K[i]; b.C[i] = C[i];
         if ((int64_t)K[i] * C[i] > mx) mx = (int64_t)K[i] * C[i];
     }
-    int gx = (int)((mx + 255) / 256);
+    int gx = (int)((mx / 2 + 255) / 256);
     if (gx > 256) gx = 256;
     weights_to_planes_batch_kernel<<<dim3(gx, 2 * n), 256, 0, s>>>(b); clb::count_launch();
     return CLB_OK;

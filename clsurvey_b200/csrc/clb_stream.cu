@@ -165,6 +165,18 @@ mas_kernel(float* __restrict__ omega, const float* __restrict__ g, float prev, f
     }
 }
 
+// mode-IMM merge (IMM/merge.py:228-231): mean_param += (precision_k / sum_precision) * theta_k, op by op like the reference
+// (div, mul, add each rounded); first != 0 starts from the reference's torch.zeros.  Any alignment (per-tensor calls).
+__global__ void __launch_bounds__(kThreads)
+imm_merge_kernel(float* __restrict__ acc, const float* __restrict__ prec, const float* __restrict__ sum_prec,
+                 const float* __restrict__ theta, int64_t n, int first) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float d = __fmul_rn(__fdiv_rn(prec[i], sum_prec[i]), theta[i]);
+        acc[i] = __fadd_rn(first ? 0.f : acc[i], d);
+    }
+}
+
 __device__ __forceinline__ void consolidate_elem(float& om, float& w, float th, float& ts, float slack) {
     const float pd = __fsub_rn(th, ts);
     const float dom = __fadd_rn(__fmul_rn(pd, pd), slack);        // path_diff.pow(2).add_(slak)
@@ -276,6 +288,15 @@ int clb_si_consolidate(float* omega, float* w, const float* theta, float* theta_
     if (n == 0) return CLB_OK;
     si_consolidate_kernel<<<stream_grid(n >> 2), kThreads, 0, as_stream(stream)>>>(omega, w, theta, theta_star, slack,
                                                                                     n); clb::count_launch();
+    CLB_CHECK_LAUNCH();
+    return CLB_OK;
+}
+
+int clb_imm_merge_accum(float* acc, const float* prec, const float* sum_prec, const float* theta, int64_t n, int first,
+                        void* stream) {
+    CLB_CHECK_ARG(acc && prec && sum_prec && theta && n >= 0);
+    if (n == 0) return CLB_OK;
+    imm_merge_kernel<<<stream_grid((n + 3) >> 2), kThreads, 0, as_stream(stream)>>>(acc, prec, sum_prec, theta, n, first); clb::count_launch();
     CLB_CHECK_LAUNCH();
     return CLB_OK;
 }

@@ -191,6 +191,11 @@ int clb_mas_accum(float* omega, const float* g, float prev_size, float curr_size
 int clb_si_consolidate(float* omega, float* w, const float* theta, float* theta_star, float slack, int64_t n,
                        void* stream);
 
+/* mode-IMM merge (IMM/merge.py:228-231): acc (+)= (prec / sum_prec) * theta, element-wise, each op rounded like the
+ * reference's tensor ops; first != 0 overwrites acc (the reference starts from torch.zeros).  No alignment requirement. */
+int clb_imm_merge_accum(float* acc, const float* prec, const float* sum_prec, const float* theta, int64_t n, int first,
+                        void* stream);
+
 /* accumelate_reg_params (EWC/main_EWC.py:205-232):  dst = a + b*scale_b   (also used to finish a sharded pass) */
 int clb_axpby(float* dst, const float* a, const float* b, float scale_b, int64_t n, void* stream);
 

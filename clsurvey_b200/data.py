@@ -74,6 +74,7 @@ class CachedLoader:
     def __iter__(self):
         n, bs = self.x.shape[0], self.batch_size
         if not self.shuffle:
+            torch.empty((), dtype=torch.int64).random_()               # a DataLoader iterator draws its base seed even unshuffled
             for i in range(0, n, bs):
                 yield self.x[i:i + bs], self.y[i:i + bs]
             return
@@ -90,6 +91,15 @@ class PinnedLoader(CachedLoader):
 
     def __init__(self, dset, batch_size, shuffle=False):
         super().__init__(dset, batch_size, shuffle, device="cpu", pinned=True)
+
+
+class TaskTensorDataset(torch.utils.data.TensorDataset):
+    """An in-memory task in the shape the reference's pickled datasets have: (image, label) items and a `.classes` list
+    (src/data/imgfolder.py ImageFolderTrainVal).  Importable, so it survives torch.save / worker processes."""
+
+    def __init__(self, x, y, classes):
+        super().__init__(x, y)
+        self.classes = list(classes)
 
 
 def cache_enabled(dset, limit_bytes=None):

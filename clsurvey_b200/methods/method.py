@@ -6,7 +6,7 @@ class attributes name / eval_name / category / extra_hyperparams_count / hyperpa
 start_scratch / wrap_first_task_model / no_framework / grid_chkpt] and the methods grid_train / train / get_output /
 inference_eval [/ poststep].  `parse(name)` returns the same objects, so `framework.main.main(method=parse('EWC'))`
 (main.py:77,89-92 accepts injected objects) runs the reference's task loop on this engine.
-Methods outside the hot path (LwF, EBLL, IMM, PackNet, HAT, iCaRL, replay baselines, Joint) are not provided.
+IMM is provided on the same kernels; LwF, EBLL, PackNet, HAT, iCaRL, the replay baselines and Joint are not.
 """
 import copy
 import os
@@ -19,6 +19,8 @@ import torch
 from ..engine import get_engine
 from .EWC import main_EWC as trainEWC
 from .Finetune import main_SGD as trainFT
+from .IMM import main_L2transfer as trainIMM
+from .IMM import merge as mergeIMM
 from .MAS import main_MAS as trainMAS
 from .rehearsal import main_rehearsal as trainRehearsal
 from .SI import main_SI as trainSI
@@ -29,6 +31,8 @@ def parse(method_name):
     for cls in (EWC, MAS, SI, GEM, Finetune):
         if method_name == cls.name:
             return cls()
+    if IMM.name in method_name:                                       # modeIMM, meanIMM (method.py:73-76)
+        return IMM(method_name.replace('_', '').replace(IMM.name, '').strip())
     raise NotImplementedError("Method not on the B200 hot path: %s" % method_name)
 
 
@@ -233,6 +237,53 @@ class MAS(Method):
 
     def get_output(self, images, args):
         return get_output_def(args.model, args.heads, images, args.current_head_idx, args.final_layer_idx)
+
+    @staticmethod
+    def inference_eval(args, manager):
+        return Finetune.inference_eval(args, manager)
+
+
+class IMM(Method):
+    """method.py:760-819: L2-transfer training (penalised step with omega = 1), mean / mode merge before
+    evaluation."""
+    name = "IMM"
+    eval_name = name
+    modes = ['mean', 'mode']
+    category = Category.MODEL_BASED
+    extra_hyperparams_count = 1
+    hyperparams = OrderedDict({'lambda': 0.01})
+    grid_chkpt = True
+    no_framework = True
+
+    def __init__(self, mode='mode'):
+        if mode not in self.modes:
+            raise Exception("NO EXISTING IMM MODE: '{}'".format(mode))
+        self.mode = mode
+        self.eval_name = self.name + "_" + self.mode
+
+    def set_mode(self, mode):
+        if mode not in self.modes:
+            raise Exception("TRY TO SET NON EXISTING IMM MODE: ", mode)
+        self.mode = mode
+        self.eval_name = self.name + "_" + self.mode
+
+    def grid_train(self, args, manager, lr):
+        return trainIMM.fine_tune_l2transfer(dataset_path=manager.current_task_dataset_path,
+                                             model_path=manager.previous_task_model_path,
+                                             exp_dir=manager.gridsearch_exp_dir, reg_lambda=self.hyperparams['lambda'],
+                                             batch_size=args.batch_size, num_epochs=args.num_epochs, lr=lr,
+                                             weight_decay=args.weight_decay, saving_freq=args.saving_freq)
+
+    def get_output(self, images, args):
+        return get_output_def(args.model, args.heads, images, args.current_head_idx, args.final_layer_idx)
+
+    @staticmethod
+    def grid_poststep(args, manager):
+        manager.previous_task_model_path = os.path.join(manager.best_exp_grid_node_dirname, 'best_model.pth.tar')
+
+    def eval_model_preprocessing(self, args):
+        """Merging step before evaluation (method.py:808-813)."""
+        return mergeIMM.preprocess_merge_IMM(self, args.models_path, args.datasets_path, args.batch_size, overwrite=True)
 
     @staticmethod
     def inference_eval(args, manager):

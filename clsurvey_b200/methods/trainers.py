@@ -186,7 +186,7 @@ def run_train_model(flavour, model, criterion, optimizer, lr, dset_loaders, dset
 
 def _run_train_model(writer, flavour, model, criterion, optimizer, lr, dset_loaders, dset_sizes, use_gpu, num_epochs,
                      exp_dir="./", resume="", saving_freq=5, save_models_mode=True):
-    assert flavour in ("sgd", "ewc", "mas", "si")
+    assert flavour in ("sgd", "ewc", "mas", "si", "l2t")        # l2t: IMM L2-transfer = step(reg_params), no divergence exit
     eng = engine_of(model.parameters())
     si = flavour == "si"
     since = time.time()
@@ -298,7 +298,7 @@ def _run_train_model(writer, flavour, model, criterion, optimizer, lr, dset_load
             log["epochs"].append((epoch, phase, epoch_loss, epoch_acc))
             LAST_RUN.update(log)
             print("{} Loss: {:.4f} Acc: {:.4f}".format(phase, epoch_loss, epoch_acc))
-            if flavour != "sgd" and (epoch_loss > 1e4 or math.isnan(epoch_loss)):
+            if flavour not in ("sgd", "l2t") and (epoch_loss > 1e4 or math.isnan(epoch_loss)):
                 return model, best_acc
             if phase == "val":
                 if epoch_acc > best_acc:

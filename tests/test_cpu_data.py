@@ -26,8 +26,7 @@ def test_cached_loader_matches_dataloader_order():
             assert len(ld) == len(ref) == len(got)
             for (a, b), (c, d) in zip(ref + ref2, got + got2):
                 assert torch.equal(a, c) and torch.equal(b, d)
-            if shuffle:
-                assert torch.equal(torch.get_rng_state(), state_ref)   # the host generator is left in the same state
+            assert torch.equal(torch.get_rng_state(), state_ref)       # the host generator is left in the same state
 
 
 def test_generic_dataset_is_materialised_once():

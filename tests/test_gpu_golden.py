@@ -291,3 +291,69 @@ def test_wide_si_through_planes_kernels(tmp_path):
         assert rel_err(m.state_dict()[k], v) <= TOL, k
     for n, ref in r["reg_after"].items():
         assert rel_err(m.reg_params[named[n]]["w"], ref["w"]) <= 2e-3, n
+
+
+# ---------------------------------------------------------------------------------------------- IMM
+def test_imm_precision_and_merge(tmp_path):
+    """tests/golden/imm.pt (methods/IMM/merge.py run unmodified): mode-IMM precision with labels sampled from the host
+    generator (same draws as the reference: the multinomial stream is replayed), the mode merge bit-for-bit op order, and the
+    reference's mean-merge quirk (an unchanged copy of the last model)."""
+    from clsurvey_b200.engine import get_engine
+    from clsurvey_b200.methods.IMM import merge as MG
+    g = load_golden("imm")
+    models, precisions = [], []
+    for t, state in enumerate(g["states"]):
+        m = tiny_model(state)
+        get_engine(m, (3, 16, 16), BS)
+        (xt, yt), (xv, yv) = g["data"][t]
+        mk = lambda x, y: torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=BS, shuffle=False)
+        torch.manual_seed(g["seeds"][t])
+        prec = MG.diag_fisher(m, {"train": mk(xt, yt), "val": mk(xv, yv)}, exclude_params=g["head_names"])
+        assert set(prec) == set(g["precisions"][t])
+        for n, v in g["precisions"][t].items():
+            assert rel_err(prec[n], v) <= TOL, (t, n)
+        models.append(m)
+        precisions.append(g["precisions"][t])              # merge from the reference's precisions: isolates the merge kernel
+    sums = [precisions[0]]
+    for t in (1, 2):
+        sums.append({n: sums[-1][n] + precisions[t][n] for n in precisions[t]})
+    for i, upto in enumerate((1, 2)):
+        mean = MG.IMM_merge_models(models, upto, g["head_names"], mean_mode=True).state_dict()
+        mode = MG.IMM_merge_models(models, upto, g["head_names"], precision=precisions, sum_precision=sums[upto],
+                                   mean_mode=False).state_dict()
+        for k in g["merged_mean"][i]:
+            assert torch.equal(mean[k].cpu(), g["merged_mean"][i][k]), ("mean", upto, k)
+            assert rel_err(mode[k], g["merged_mode"][i][k]) <= 1e-6, ("mode", upto, k)
+
+
+def test_imm_l2_transfer_is_the_penalty_step_with_unit_omega(tmp_path):
+    """train_L2transfer.py:35-100 == train_EWC.py:46-84 with omega = 1 (main_L2transfer.py:41,58): the L2-transfer entry
+    point reproduces an EWC-style run of the oracle with unit omega, including its fresh head being registered."""
+    import copy
+    from oracle import restate
+    from clsurvey_b200.methods import method as M
+    from clsurvey_b200.methods.IMM import main_L2transfer as L
+    g = load_golden("finetune")["wd0"]
+    torch.manual_seed(5)
+    base = tiny_model(g["init"])
+    mp = str(tmp_path / "prev.pth.tar")
+    torch.save(base, mp)
+    xt, yt, xv, yv = g["data"]
+
+    class DS(torch.utils.data.TensorDataset):
+        classes = list(range(NCLS))
+    dsets = {"train": DS(xt, yt), "val": DS(xv, yv)}
+    torch.manual_seed(77)
+    model, acc = L.fine_tune_l2transfer(dsets, mp, str(tmp_path / "exp"), batch_size=BS, num_epochs=2, lr=0.05, reg_lambda=0.5)
+    # oracle: same head draw, omega = 1 everywhere, theta* = theta at the start, same shuffled batches
+    ref = tiny_model(g["init"])
+    torch.manual_seed(77)
+    ref.classifier._modules["4"] = nn.Linear(32, NCLS)
+    reg = [dict(omega=torch.ones_like(p), init_val=p.data.clone()) for p in ref.parameters()]
+    tr = restate.Trainer(ref, "penalty", 0.05, reg=reg, lam=0.5)
+    mk = lambda x, y: torch.utils.data.DataLoader(torch.utils.data.TensorDataset(x, y), batch_size=BS, shuffle=True)
+    best, _, _ = tr.train_model({"train": mk(xt, yt), "val": mk(xv, yv)}, {"train": len(xt), "val": len(xv)}, 2)
+    assert acc == best
+    for k, v in ref.state_dict().items():
+        assert rel_err(model.state_dict()[k], v) <= TOL, k
+    assert isinstance(M.parse("modeIMM"), M.IMM) and M.parse("meanIMM").mode == "mean"

@@ -192,3 +192,37 @@ def test_two_heads_round_trip_do_not_alias():
     assert torch.equal(head_b.weight.detach().cpu(), wb)
     m.classifier._modules["4"] = head_b
     assert torch.equal(get_engine(m).forward(x), logits_b)
+
+
+def test_lr_grid_concurrent_replicas_match_sequential(tmp_path):
+    """f-4: the learning-rate grid (src/framework/lr_grid_train.py:9-160) with its nodes trained as concurrent processes gives
+    the accuracies, the best lr and the files of the node-by-node loop: every node is seeded by its iteration index
+    (lr_grid_train.py:73,77), so where and when it runs does not matter."""
+    from clsurvey_b200.framework import lr_grid_train as G
+    from clsurvey_b200.methods import method as M
+    from clsurvey_b200.utilities import utils
+    lrs = [0.05, 0.01]
+    common = dict(current_task_dataset_path=_save_task(tmp_path, "t2", 21), previous_task_model_path=_first_model(tmp_path))
+    args = types.SimpleNamespace(lrs=lrs, finetune_iterations=2, task_counter=2, batch_size=BS, num_epochs=2, weight_decay=0.0,
+                                 saving_freq=1)
+    manager = types.SimpleNamespace(method=M.Finetune(), parent_exp_dir=str(tmp_path / "par"), **common)
+    best_lr, best_acc = G.lr_grid_single_task(args, manager, save_models_mode="all", gpus=1)
+    ck = torch.load(os.path.join(manager.ft_parent_exp_dir, "grid_checkpoint.pth"), weights_only=False)["processed_lrs"]
+    # sequential reference: the same nodes one after the other in this process
+    seq = {}
+    for lr in lrs:
+        for it in range(2):
+            utils.set_random(it)
+            m2 = types.SimpleNamespace(method=M.Finetune(), gridsearch_exp_dir=str(tmp_path / ("seq_%g_%d" % (lr, it))), **common)
+            _, acc = M.Finetune.grid_train(args, m2, lr)
+            seq[(lr, it)] = acc
+    for lr in lrs:
+        assert ck[lr]["acc"] == [seq[(lr, 0)], seq[(lr, 1)]], (lr, ck[lr], seq)
+    avg = {lr: (seq[(lr, 0)] + seq[(lr, 1)]) / 2 for lr in lrs}
+    exp_best = max(lrs, key=lambda l: (avg[l], -lrs.index(l)))           # first lr wins ties (strict '>' in the reference)
+    assert best_lr == exp_best and abs(best_acc - avg[exp_best]) < 1e-12
+    assert os.path.isfile(os.path.join(manager.best_exp_grid_node_dirname, "best_model.pth.tar"))
+    assert manager.previous_task_model_path == os.path.join(manager.best_exp_grid_node_dirname, "best_model.pth.tar")
+    # resumed grid: nothing left to train, same answer from the checkpoint
+    manager2 = types.SimpleNamespace(method=M.Finetune(), parent_exp_dir=str(tmp_path / "par"), **common)
+    assert G.lr_grid_single_task(args, manager2, save_models_mode="all", gpus=1) == (best_lr, best_acc)

@@ -29,26 +29,47 @@ gem_dots_gram_kernel(const float* __restrict__ g, const float* __restrict__ G, i
 #pragma unroll
     for (int i = 0; i < K; ++i) rows[i] = G + (int64_t)idx[i] * ld;
 
+    // Products and short partial sums in fp32 (the reference's torch.mm accumulates ALL of P in fp32, gem.py:275-276), flushed
+    // into the fp64 accumulators every U float4 groups (<= 16 terms per partial sum: the fp32 rounding of such a partial is
+    // ~1e-7 of its own magnitude and unbiased).  U independent groups of loads are in flight per thread; with the fp64 FMAs
+    // of the first version the kernel was bound by the DFMA pipe at every k (58-61 % of HBM, profiles/r1_stream_kernels.jsonl).
+    constexpr int U = K <= 3 ? 4 : 2;
     const int64_t n4 = P >> 2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        const float4 gv = __ldcs(reinterpret_cast<const float4*>(g) + i);
-        float4 m[K];
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += stride * U) {
+        float4 gv[U], m[U][K];
 #pragma unroll
-        for (int a = 0; a < K; ++a) m[a] = __ldcs(reinterpret_cast<const float4*>(rows[a]) + i);
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + (int64_t)u * stride;
+            const bool ok = i < n4;
+            gv[u] = ok ? __ldcs(reinterpret_cast<const float4*>(g) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int a = 0; a < K; ++a) {
-            acc_d[a] += (double)gv.x * m[a].x + (double)gv.y * m[a].y + (double)gv.z * m[a].z + (double)gv.w * m[a].w;
+            for (int a = 0; a < K; ++a)
+                m[u][a] = ok ? __ldcs(reinterpret_cast<const float4*>(rows[a]) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        int p = 0;
+        float s_d[K], s_g[NPAIR];
 #pragma unroll
-        for (int a = 0; a < K; ++a)
+        for (int a = 0; a < K; ++a) s_d[a] = 0.f;
 #pragma unroll
-            for (int b = a; b < K; ++b) {
-                acc_g[p] += (double)m[a].x * m[b].x + (double)m[a].y * m[b].y + (double)m[a].z * m[b].z +
-                            (double)m[a].w * m[b].w;
-                ++p;
-            }
+        for (int a = 0; a < NPAIR; ++a) s_g[a] = 0.f;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int a = 0; a < K; ++a)
+                s_d[a] = fmaf(gv[u].x, m[u][a].x, fmaf(gv[u].y, m[u][a].y, fmaf(gv[u].z, m[u][a].z, fmaf(gv[u].w, m[u][a].w, s_d[a]))));
+            int p = 0;
+#pragma unroll
+            for (int a = 0; a < K; ++a)
+#pragma unroll
+                for (int b = a; b < K; ++b) {
+                    s_g[p] = fmaf(m[u][a].x, m[u][b].x, fmaf(m[u][a].y, m[u][b].y, fmaf(m[u][a].z, m[u][b].z, fmaf(m[u][a].w, m[u][b].w, s_g[p]))));
+                    ++p;
+                }
+        }
+#pragma unroll
+        for (int a = 0; a < K; ++a) acc_d[a] += (double)s_d[a];
+#pragma unroll
+        for (int a = 0; a < NPAIR; ++a) acc_g[a] += (double)s_g[a];
     }
     if (blockIdx.x == 0 && threadIdx.x < (P & 3)) {  // scalar tail
         const int64_t e = (n4 << 2) + threadIdx.x;

@@ -152,7 +152,12 @@ class Net(nn.Module):
         o1, o2 = self.compute_offsets(t, self.cum_nc_per_task)
         B = y.size(0)
         lo, hi = cdist.shard_rows(B)
-        eng.fwd_loss_bwd(x[lo:hi], y[lo:hi], LOSS_MEAN_CE, denom=B, train=True, masks=masks, col_off=o1, ncols=o2 - o1)
+        if hi > lo:
+            eng.fwd_loss_bwd(x[lo:hi], y[lo:hi], LOSS_MEAN_CE, denom=B, train=True, masks=masks, col_off=o1, ncols=o2 - o1)
+        else:                                           # B < world: this rank's shard is empty -> zero gradient, same collectives
+            eng.backward_skip()
+            eng.loss_dev.zero_()
+            eng.correct_dev.zero_()
         loss, correct = eng.loss_dev.clone(), eng.correct_dev.clone()
         cdist.allreduce_grads(eng)
         viol = None
@@ -181,8 +186,13 @@ class Net(nn.Module):
         o1, o2 = self.compute_offsets(t, self.cum_nc_per_task)
         B = y.size(0)
         lo, hi = cdist.shard_rows(B)
-        eng.fwd_loss_bwd(x[lo:hi], y[lo:hi], LOSS_MEAN_CE, denom=B, train=self.net.training,
-                         masks=self._unit_masks(eng), col_off=o1, ncols=o2 - o1)
+        if hi > lo:
+            eng.fwd_loss_bwd(x[lo:hi], y[lo:hi], LOSS_MEAN_CE, denom=B, train=self.net.training,
+                             masks=self._unit_masks(eng), col_off=o1, ncols=o2 - o1)
+        else:
+            eng.backward_skip()
+            eng.loss_dev.zero_()
+            eng.correct_dev.zero_()
         loss, correct = eng.loss_dev.clone(), eng.correct_dev.clone()
         self.opt.step()
         return loss, correct

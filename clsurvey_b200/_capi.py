@@ -64,9 +64,6 @@ SIGNATURES = {
     "clb_gem_solve_qp": [c_p, c_p, c_i, c_d, c_d, c_p, c_p, c_p],
     "clb_gem_solve_qp_host": [c_p, c_p, c_i, c_d, c_d, c_p, c_p],
     "clb_gem_project": [c_p, c_p, c_i64, c_i64, c_p, c_i, c_p, c_p, c_p],
-    "clb_debug_umma_mn": [c_p, c_p, c_p, c_i, c_p],
-    "clb_debug_umma_bf16": [c_p, c_p, c_p, c_i, c_p],
-    "clb_debug_tma3d": [c_p] + [c_i] * 10 + [c_p, c_p],
     "clb_nccl_unique_id": [c_p],
     "clb_nccl_init": [c_p, c_i, c_i, c_p],
     "clb_nccl_allreduce_f32": [c_p, c_p, c_i64, c_p],

@@ -92,5 +92,18 @@ def _build_variant(extra, out_name):
     return lib
 
 
+def build_probe():
+    """Bring-up probes (csrc/probe/clb_debug.cu: MN-major descriptor, bf16 operand conventions, TMA box behaviour) as their own
+    library _lib/libclb_probe.so -- test tooling for tools/*_probe.py, not part of the product ABI (include/clb.h)."""
+    os.makedirs(OUT_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    lib = os.path.join(OUT_DIR, "libclb_probe.so")
+    srcs = [os.path.join(CSRC, "probe", "clb_debug.cu"), os.path.join(CSRC, "clb_tma.cu"), os.path.join(CSRC, "clb_core.cu")]
+    r = subprocess.run([nvcc] + ARCH + FLAGS + ["-shared", "-o", lib] + srcs + ["-ldl"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(r.stderr)
+    return lib
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))

@@ -9,275 +9,16 @@
 //     a*b ~= hi_a*hi_b + lo_a*hi_b + hi_a*lo_b      (dropped lo*lo term <= 2^-20 relative), fp32 accumulation in TMEM.
 // CLB_MM_TF32X1 issues only the hi*hi pass (fast, NOT parity mode).
 //
-// Operands are gathered by loader warps straight from the reference's NCHW / [K,C,R,S]-derived layouts (LDG ->
-// split -> swizzled STS.128, nothing is materialised in HBM); a single elected thread issues tcgen05.mma; smem stages
-// are recycled through mbarriers signalled by tcgen05.commit; the epilogue reads the accumulator with tcgen05.ld.
+// This file holds the host-side dispatch of the NCHW tensor-core kernels (clb_gemm_tc2.cu: A through TMEM; clb_gemm_tc3.cu:
+// TMA-fed weights / dY; clb_gemm_tc4.cu: bf16 hi/lo split) and their helper kernels (weight re-ordering, split-K reduce).
+// They serve the layers the planes pipeline (clb_planes_*.cu) does not take: nets with C % 64 != 0, AlexNet, Linear.
 // GEMM-K order is (r, s, c) so that one 32-wide K block has a single (r, s): one bounds test per block per pixel.
-//
-// Warp roles (288 threads): warps 0-3 load even K blocks, warps 4-7 load odd K blocks (two groups keep two blocks of
-// global loads in flight), warp 8 allocates TMEM and issues the MMAs; warps 0-7 then run the epilogue.
 #include <stdlib.h>
 
 #include "clb_tc_ptx.cuh"
 
 namespace clb {
 namespace tc {
-
-constexpr int kThreads = 288;
-
-// store one 4-float chunk (row r, 16-byte chunk c) of a K block into the swizzled hi / lo tiles
-template <bool WITH_LO>
-__device__ __forceinline__ void store_chunk(uint32_t tile_hi, uint32_t tile_lo, int r, int c, float v0, float v1, float v2,
-                                            float v3) {
-    const uint32_t off = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
-    const uint32_t h0 = __float_as_uint(v0) & kHiMask, h1 = __float_as_uint(v1) & kHiMask;
-    const uint32_t h2 = __float_as_uint(v2) & kHiMask, h3 = __float_as_uint(v3) & kHiMask;
-    st_shared_v4(tile_hi + off, h0, h1, h2, h3);
-    if (WITH_LO) {
-        st_shared_v4(tile_lo + off, __float_as_uint(v0 - __uint_as_float(h0)), __float_as_uint(v1 - __uint_as_float(h1)),
-                     __float_as_uint(v2 - __uint_as_float(h2)), __float_as_uint(v3 - __uint_as_float(h3)));
-    }
-}
-
-// ---------------------------------------------------------------------------------------------- operand loaders
-// Each loader fills a [ROWS x 32] K block: fill<WITH_LO>(kb, tg, row0, tile_hi, tile_lo), tg = thread in group (0..127).
-
-// (1) pixel rows gathered from an NCHW tensor: row = output pixel, K = (r, s, c); used for A of fwd / dgrad.
-struct PixelGather {
-    const float* x; int C, H, W, R, S, pad, P, Q, M;    // M = N_img * P * Q rows in total; stride 1
-    FastDiv32 dPQ, dQ, dC, dS;
-    template <bool WITH_LO>
-    __device__ __forceinline__ void fill(int kb, int tg, int row0, uint32_t tile_hi, uint32_t tile_lo) const {
-        const int m = row0 + tg;                         // one full 128-byte row per thread
-        const uint32_t k0 = (uint32_t)kb * BK;
-        const uint32_t rs = dC.div(k0), c0 = k0 - rs * C;
-        const uint32_t r = dS.div(rs), s = rs - r * S;
-        const uint32_t img = dPQ.div(m), pq = m - img * (P * Q);
-        const uint32_t p = dQ.div(pq), q = pq - p * Q;
-        const int ih = (int)p + (int)r - pad, iw = (int)q + (int)s - pad;
-        const bool ok = m < M && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W;
-        const float* src = x + ((size_t)img * C + c0) * H * W + (ok ? ih * W + iw : 0);
-        const int HW = H * W;
-        float v[BK];
-#pragma unroll
-        for (int j = 0; j < BK; ++j) v[j] = ok ? __ldg(src + (size_t)j * HW) : 0.f;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) store_chunk<WITH_LO>(tile_hi, tile_lo, tg, c, v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-    }
-};
-
-// (2) rows that are contiguous along K in memory (16-byte aligned chunks): weights [rows][ldk] (B of fwd / dgrad) and
-//     dY viewed as [kout][pixel] with an image stride (A of wgrad: addr = img*img_stride + row*ld + pq).
-template <int ROWS>
-struct RowsKContig {
-    const float* p; int n_rows; int64_t ld; int k_total; int pq; int64_t img_stride; FastDiv32 dPQ;   // pq == 0: plain matrix
-    template <bool WITH_LO>
-    __device__ __forceinline__ void fill(int kb, int tg, int row0, uint32_t tile_hi, uint32_t tile_lo) const {
-        const int chunk = tg & 7;
-        const int kk = kb * BK + chunk * 4;
-        int64_t koff = kk;
-        if (pq != 0) {
-            const uint32_t img = dPQ.div(kk);
-            koff = (int64_t)img * img_stride + (kk - (int)img * pq);
-        }
-        const bool kok = kk < k_total;
-        float4 v[ROWS / 16];
-#pragma unroll
-        for (int i = 0; i < ROWS / 16; ++i) {
-            const int r = (tg >> 3) + 16 * i;
-            const bool ok = kok && (row0 + r) < n_rows;
-            v[i] = ok ? __ldg(reinterpret_cast<const float4*>(p + (int64_t)(row0 + r) * ld + koff)) : make_float4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int i = 0; i < ROWS / 16; ++i)
-            store_chunk<WITH_LO>(tile_hi, tile_lo, (tg >> 3) + 16 * i, chunk, v[i].x, v[i].y, v[i].z, v[i].w);
-    }
-};
-
-// (3) im2col rows over pixels: row = (r, s, c) filter tap, K = pixel; B of wgrad.
-template <int ROWS>
-struct TapRowsOverPixels {
-    const float* x; int C, H, W, R, S, pad, P, Q, n_rows, k_total;     // n_rows = R*S*C, k_total = N_img*P*Q
-    FastDiv32 dPQ, dQ, dC, dS;
-    template <bool WITH_LO>
-    __device__ __forceinline__ void fill(int kb, int tg, int row0, uint32_t tile_hi, uint32_t tile_lo) const {
-        const int chunk = tg & 7;
-        const int pix = kb * BK + chunk * 4;             // 4 consecutive pixels of one image row (Q % 4 == 0)
-        const uint32_t img = dPQ.div(pix), pq = pix - img * (P * Q);
-        const uint32_t p = dQ.div(pq), q0 = pq - p * Q;
-        const bool kok = pix < k_total;
-        const float* img_base = x + (size_t)img * C * H * W;
-        float v[ROWS / 16][4];
-#pragma unroll
-        for (int i = 0; i < ROWS / 16; ++i) {
-            const int n = row0 + (tg >> 3) + 16 * i;
-            const uint32_t rs = dC.div(n), c = n - rs * C;
-            const uint32_t r = dS.div(rs), s = rs - r * S;
-            const int ih = (int)p + (int)r - pad;
-            const int iw0 = (int)q0 + (int)s - pad;
-            const bool rok = kok && n < n_rows && (unsigned)ih < (unsigned)H;
-            const float* src = img_base + ((size_t)c * H + (rok ? ih : 0)) * W;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int iw = iw0 + j;
-                v[i][j] = (rok && (unsigned)iw < (unsigned)W) ? __ldg(src + iw) : 0.f;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < ROWS / 16; ++i)
-            store_chunk<WITH_LO>(tile_hi, tile_lo, (tg >> 3) + 16 * i, chunk, v[i][0], v[i][1], v[i][2], v[i][3]);
-    }
-};
-
-// ---------------------------------------------------------------------------------------------- epilogues
-struct EpiNCHW {     // y[img][n][pq] = act(acc + bias[n]);  row m = img*PQ + pq  (lanes = consecutive pixels: coalesced)
-    float* y; const float* bias; int relu, M, N, PQ; FastDiv32 dPQ;
-    __device__ __forceinline__ void store16(int m, int n0, const uint32_t (&r)[16], int /*z*/) const {
-        if (m >= M) return;
-        const uint32_t img = dPQ.div(m), pq = m - img * PQ;
-        float* dst = y + ((size_t)img * N + n0) * PQ + pq;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            if (n0 + j < N) {
-                float v = __uint_as_float(r[j]) + (bias ? __ldg(bias + n0 + j) : 0.f);
-                dst[(size_t)j * PQ] = relu ? fmaxf(v, 0.f) : v;
-            }
-        }
-    }
-};
-struct EpiSplitK {   // ws[z][m][n] row-major partial sums (wgrad); reduced in fixed order by a second kernel
-    float* ws; int M, N; int64_t split_stride;
-    __device__ __forceinline__ void store16(int m, int n0, const uint32_t (&r)[16], int z) const {
-        if (m >= M) return;
-        float* dst = ws + (int64_t)z * split_stride + (int64_t)m * N + n0;
-        if (n0 + 15 < N && (N & 3) == 0) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                  __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-        } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (n0 + j < N) dst[j] = __uint_as_float(r[j]);
-        }
-    }
-};
-
-// ---------------------------------------------------------------------------------------------- the kernel
-template <int BN, int STAGES, bool WITH_LO> struct SmemLayout {
-    static constexpr int kATile = BM * 128, kBTile = BN * 128;
-    static constexpr int kStage = (kATile + kBTile) * (WITH_LO ? 2 : 1);
-    static constexpr int kBarOff = kStage * STAGES;
-    static constexpr int kTotal = kBarOff + 256 + 1024;     // barriers + tmem slot, + slack for 1024-B alignment
-};
-
-template <int BN, int STAGES, bool WITH_LO, class ALoad, class BLoad, class Epi>
-__global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(ALoad A, BLoad B, Epi epi, int num_kb_total, int kb_per_split) {
-    using L = SmemLayout<BN, STAGES, WITH_LO>;
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_full = base + L::kBarOff, bar_empty = bar_full + 8 * STAGES, bar_tmem = bar_empty + 8 * STAGES;
-    const uint32_t tmem_slot = bar_tmem + 8;
-    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, z = blockIdx.z;
-    const int kb_begin = z * kb_per_split;
-    const int kb_end = min(num_kb_total, kb_begin + kb_per_split);
-    const int nkb = max(kb_end - kb_begin, 0);
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(bar_full + 8 * s, 4);       // one arrive per loader warp of the owning group
-            mbar_init(bar_empty + 8 * s, 1);      // tcgen05.commit
-        }
-        mbar_init(bar_tmem, 1);
-        fence_barrier_init();
-    }
-    // two accumulators when splitting: columns [0,BN) take hi*hi, columns [BN,2BN) take the ~2^-11 smaller cross terms.
-    // The tensor core's fp32 accumulate truncates; keeping the small terms apart cuts the number of (biased) roundings
-    // applied to the large accumulator by 3x.
-    constexpr uint32_t kTmemCols = WITH_LO ? 2 * BN : BN;
-    if (warp == 8) tmem_alloc(tmem_slot, kTmemCols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot_ptr;
-
-    if (warp < 8) {
-        // ---------------- loaders: group g handles K blocks with (i % 2) == g
-        const int group = warp >> 2, tg = threadIdx.x & 127;
-        for (int i = group; i < nkb; i += 2) {
-            const int s = i % STAGES;
-            const uint32_t it = (uint32_t)(i / STAGES);
-            mbar_wait(bar_empty + 8 * s, (it & 1u) ^ 1u);
-            const uint32_t st = base + (uint32_t)s * L::kStage;
-            const uint32_t a_hi = st, b_hi = st + L::kATile;
-            const uint32_t a_lo = st + L::kATile + L::kBTile, b_lo = a_lo + L::kATile;
-            A.template fill<WITH_LO>(kb_begin + i, tg, m0, a_hi, a_lo);
-            B.template fill<WITH_LO>(kb_begin + i, tg, n0, b_hi, b_lo);
-            fence_proxy_async();                   // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_full + 8 * s);
-        }
-    } else if (lane == 0) {
-        // ---------------- MMA issuer (one thread)
-        constexpr uint32_t idesc = make_idesc(BN);
-        for (int i = 0; i < nkb; ++i) {
-            const int s = i % STAGES;
-            const uint32_t it = (uint32_t)(i / STAGES);
-            mbar_wait(bar_full + 8 * s, it & 1u);
-            tc_fence_after();
-            const uint32_t st = base + (uint32_t)s * L::kStage;
-            const uint64_t a_hi = make_desc(st), b_hi = make_desc(st + L::kATile);
-            const uint64_t a_lo = make_desc(st + L::kATile + L::kBTile), b_lo = make_desc(st + 2 * L::kATile + L::kBTile);
-#pragma unroll
-            for (int k = 0; k < BK / 8; ++k) {     // +32 bytes (>>4 = 2) per K=8 step inside the swizzle row
-                if (WITH_LO) {
-                    umma_tf32(tmem_base + BN, a_lo + 2 * k, b_hi + 2 * k, idesc, (i | k) != 0);
-                    umma_tf32(tmem_base + BN, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
-                    umma_tf32(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, (i | k) != 0);
-                } else {
-                    umma_tf32(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, (i | k) != 0);
-                }
-            }
-            umma_commit(bar_empty + 8 * s);        // frees the smem stage once these MMAs have read it
-        }
-        umma_commit(bar_tmem);                     // accumulator complete
-    }
-
-    if (warp < 8) {
-        // ---------------- epilogue: warp w owns TMEM lanes 32*(w%4).., column half (w/4)
-        if (nkb > 0) {
-            mbar_wait(bar_tmem, 0);
-            tc_fence_after();
-        }
-        const int lane_grp = warp & 3, col_half = warp >> 2;
-        const int m = m0 + lane_grp * 32 + lane;
-#pragma unroll 1
-        for (int c = 0; c < BN / 2; c += 16) {
-            const int col = col_half * (BN / 2) + c;
-            uint32_t r[16];
-            if (nkb > 0) {
-                tmem_ld16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)col, r);
-                if (WITH_LO) {
-                    uint32_t r2[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(BN + col), r2);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) r[j] = 0u;
-            }
-            epi.store16(m, n0 + col, r, z);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, kTmemCols);
-}
 
 // ---------------------------------------------------------------------------------------------- helper kernels
 // w[K][C][RS] -> w2[K][ld] with w2[k][rs*C + c]   (forward GEMM-B, K order (r,s,c)); ld > RS*C zero-pads the row
@@ -328,23 +69,6 @@ __global__ void splitk_reduce_permute_kernel(const float* __restrict__ ws, float
     }
 }
 
-template <int BN, int STAGES, bool WITH_LO, class ALoad, class BLoad, class Epi>
-static int launch(const ALoad& A, const BLoad& B, const Epi& e, dim3 grid, int nkb_total, int kb_per_split, cudaStream_t s) {
-    using L = SmemLayout<BN, STAGES, WITH_LO>;
-    auto kern = gemm_tc_kernel<BN, STAGES, WITH_LO, ALoad, BLoad, Epi>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
-        if (err != cudaSuccess) {
-            set_error("cudaFuncSetAttribute(smem=%d): %s", L::kTotal, cudaGetErrorString(err));
-            return CLB_ECUDA;
-        }
-        configured = true;
-    }
-    kern<<<grid, kThreads, L::kTotal, s>>>(A, B, e, nkb_total, kb_per_split); clb::count_launch();
-    return CLB_OK;
-}
-
 static inline int ew_blocks(int64_t n) {
     int64_t b = (n + 255) / 256, cap = (int64_t)sm_count() * 8;
     return (int)(b > cap ? cap : (b < 1 ? 1 : b));
@@ -368,13 +92,13 @@ int tc3_conv_fwd(const float* x, const float* w2, const float* w2_lo, const floa
 int tc3_conv_wgrad(const float* x, const float* dy, float* ws_partials, float* bias_part, float* dy_lo, int N, int C, int H, int W,
                    int K, int R, int S, int pad, bool with_lo, int splits, int kb_per_split, cudaStream_t s);
 
-// CLB_TC_IMPL: 1 = first generation (both operands gathered into smem), 2 = A through TMEM, 3 (default) = gen-2 plus
-// TMA-fed kernels where the memory layout allows it (wgrad on >= 8x8 maps)
+// CLB_TC_IMPL: 2 = A through TMEM (clb_gemm_tc2.cu), 3 (default) = gen-2 plus TMA-fed kernels where the memory layout allows
+// it (wgrad on >= 8x8 maps).  The first generation (both operands gathered into smem) was removed in round 2.
 static int tc_impl() {
     static int v = 0;
     if (v == 0) {
         const char* e = getenv("CLB_TC_IMPL");
-        v = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 3;
+        v = (e && e[0] >= '2' && e[0] <= '3') ? (e[0] - '0') : 3;
     }
     return v;
 }
@@ -405,14 +129,14 @@ bool tc_fwd_supported(int C, int H, int W, int K, int R, int S, int stride, int 
     // exact-fp32 SIMT kernel is faster (158 us vs 256 us at batch 200); opt-in only
     static int small_c = -1;
     if (small_c < 0) { const char* e = getenv("CLB_TC_SMALLC"); small_c = (e && e[0] == '1') ? 1 : 0; }
-    return small_c && tc_impl() >= 2 && C * R * S <= 32;
+    return small_c && C * R * S <= 32;
 }
 bool tc_dgrad_supported(int C, int H, int W, int K, int R, int S, int stride, int pad) {
     return same_conv(H, W, R, S, stride, pad) && (K % 32) == 0;
 }
 bool tc_wgrad_supported(int C, int H, int W, int K, int R, int S, int stride, int pad) {
     if (!same_conv(H, W, R, S, stride, pad) || (W % 4) != 0) return false;
-    return tc_impl() >= 2 || (C % 32) == 0;
+    return true;
 }
 
 size_t tc_weight_ws_floats(int C, int K, int R, int S) { return (size_t)K * C * R * S; }
@@ -426,19 +150,7 @@ int tc_conv_fwd(const float* x, const float* w2 /*[K][RS][C]*/, const float* bia
         const size_t plane = tc_w_plane_floats(K, C, R, S);
         return tc3_conv_fwd(x, w2, w2 + plane, bias, y, N, C, H, W, K, R, S, pad, relu, with_lo, s);
     }
-    if (tc_impl() >= 2) return tc2_conv_fwd(x, w2, bias, y, N, C, H, W, K, R, S, pad, relu, with_lo, s);
-    const int P = H, Q = W, M = N * P * Q;
-    PixelGather A{x, C, H, W, R, S, pad, P, Q, M, FastDiv32(P * Q), FastDiv32(Q), FastDiv32(C), FastDiv32(S)};
-    EpiNCHW e{y, bias, relu, M, K, P * Q, FastDiv32(P * Q)};
-    const int nkb = R * S * C / BK;
-    if (K % 128 == 0 || K > 64) {
-        RowsKContig<128> B{w2, K, (int64_t)R * S * C, R * S * C, 0, 0, FastDiv32(1)};
-        dim3 grid((M + BM - 1) / BM, (K + 127) / 128, 1);
-        return with_lo ? launch<128, 3, true>(A, B, e, grid, nkb, nkb, s) : launch<128, 4, false>(A, B, e, grid, nkb, nkb, s);
-    }
-    RowsKContig<64> B{w2, K, (int64_t)R * S * C, R * S * C, 0, 0, FastDiv32(1)};
-    dim3 grid((M + BM - 1) / BM, (K + 63) / 64, 1);
-    return with_lo ? launch<64, 4, true>(A, B, e, grid, nkb, nkb, s) : launch<64, 4, false>(A, B, e, grid, nkb, nkb, s);
+    return tc2_conv_fwd(x, w2, bias, y, N, C, H, W, K, R, S, pad, relu, with_lo, s);
 }
 
 void tc_wgrad_plan(int N, int C, int H, int W, int K, int R, int S, int* bn, int* splits, int* kb_per_split) {
@@ -494,21 +206,7 @@ int tc_conv_wgrad(const float* x, const float* dy, float* dw, float* ws, float* 
         return CLB_OK;
     }
     tc_wgrad_plan(N, C, H, W, K, R, S, &bn, &splits, &per);
-    const int nkb = (npix + BK - 1) / BK;
-    RowsKContig<128> A{dy, K, (int64_t)P * Q, npix, P * Q, (int64_t)K * P * Q, FastDiv32(P * Q)};
-    EpiSplitK e{ws, K, n_rows, (int64_t)K * n_rows};
-    int rc;
-    if (tc_impl() >= 2) {
-        rc = tc2_conv_wgrad(x, dy, ws, N, C, H, W, K, R, S, pad, with_lo, s);
-    } else if (bn == 128) {
-        TapRowsOverPixels<128> B{x, C, H, W, R, S, pad, P, Q, n_rows, npix, FastDiv32(P * Q), FastDiv32(Q), FastDiv32(C), FastDiv32(S)};
-        dim3 grid((K + BM - 1) / BM, (n_rows + 127) / 128, splits);
-        rc = with_lo ? launch<128, 3, true>(A, B, e, grid, nkb, per, s) : launch<128, 4, false>(A, B, e, grid, nkb, per, s);
-    } else {
-        TapRowsOverPixels<64> B{x, C, H, W, R, S, pad, P, Q, n_rows, npix, FastDiv32(P * Q), FastDiv32(Q), FastDiv32(C), FastDiv32(S)};
-        dim3 grid((K + BM - 1) / BM, (n_rows + 63) / 64, splits);
-        rc = with_lo ? launch<64, 4, true>(A, B, e, grid, nkb, per, s) : launch<64, 4, false>(A, B, e, grid, nkb, per, s);
-    }
+    const int rc = tc2_conv_wgrad(x, dy, ws, N, C, H, W, K, R, S, pad, with_lo, s);
     if (rc) return rc;
     splitk_reduce_permute_kernel<<<ew_blocks((int64_t)K * n_rows), 256, 0, s>>>(ws, dw, K, C, R * S, splits); clb::count_launch();
     return CLB_OK;

@@ -79,7 +79,7 @@ __device__ __forceinline__ void split_pair(float v0, float v1, uint32_t& hi, uin
 // PixelRows with the plane size H*W as a compile-time constant: the 64 loads of a K block then address
 // [one 64-bit base + immediate offset] instead of carrying ~3 address instructions each (static SASS count of the loader
 // loop: ~500 -> ~300 instructions per thread and K block; the loop is issue-bound, profiles/README.md).
-// Opt-in (CLB_BF16_HWSPEC=1) until it has been measured on the GPU.
+// Default since round 2 (measured on B200: VGG-11 step 4.11 -> 3.82 ms, GPU suite green); CLB_BF16_HWSPEC=0 selects the generic loader.
 template <int HWC>
 struct PixelRowsHW {
     const float* x; int C, H, W, R, S, pad, P, Q, M;
@@ -501,16 +501,11 @@ int tc4_conv_wgrad(const float* x, const float* dy, float* ws_partials, float* b
     TapChunks B{x, C, H, W, R, S, pad, n_rows, npix, FastDiv32(PQ), FastDiv32(W), FastDiv32(C), FastDiv32(S)};
     clb::tcl::EpiSplitK e{ws_partials, K, n_rows, (int64_t)K * n_rows};
     dim3 grid((K + BM - 1) / BM, (n_rows + 127) / 128, splits);
-    static int branchy = -1;
-    if (branchy < 0) { const char* ev = getenv("CLB_BF16_WGRAD_BRANCHY"); branchy = (ev && ev[0] == '1') ? 1 : 0; }
-    static bool configured[2] = {false, false};
-    if (branchy) {
-        if (!configured[1]) { CLB_CUDA(cudaFuncSetAttribute(wgrad_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem)); configured[1] = true; }
-        wgrad_bf16_kernel<true><<<grid, kWgThreads, kWgSmem, s>>>(m_hi, m_lo, B, e, PQ / BK2, nkb, per); clb::count_launch();
-    } else {
-        if (!configured[0]) { CLB_CUDA(cudaFuncSetAttribute(wgrad_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem)); configured[0] = true; }
-        wgrad_bf16_kernel<false><<<grid, kWgThreads, kWgSmem, s>>>(m_hi, m_lo, B, e, PQ / BK2, nkb, per); clb::count_launch();
-    }
+    // (the straight-line "BRANCHY" store variant was timed on B200 in round 2: 4.104 vs 4.107 ms/step -- no gain, removed from
+    // the dispatch; the template parameter stays false)
+    static bool configured = false;
+    if (!configured) { CLB_CUDA(cudaFuncSetAttribute(wgrad_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem)); configured = true; }
+    wgrad_bf16_kernel<false><<<grid, kWgThreads, kWgSmem, s>>>(m_hi, m_lo, B, e, PQ / BK2, nkb, per); clb::count_launch();
     return CLB_OK;
 }
 
@@ -529,7 +524,7 @@ int tc4_conv_fwd(const float* x, const void* w_hi, const void* w_lo, const float
     const uint16_t* wl = static_cast<const uint16_t*>(w_lo);
     const bool wide = (K % 128 == 0 || K > 64);
     static int hwspec = -1;
-    if (hwspec < 0) { const char* ev = getenv("CLB_BF16_HWSPEC"); hwspec = (ev && ev[0] == '1') ? 1 : 0; }
+    if (hwspec < 0) { const char* ev = getenv("CLB_BF16_HWSPEC"); hwspec = (ev && ev[0] == '0') ? 0 : 1; }   // default on: measured 4.11 -> 3.82 ms/step (round 2, gpurun r2a)
     if (hwspec) {
 #define CLB_HW_CASE(HWV)                                                                                              \
         case HWV: {                                                                                                       \

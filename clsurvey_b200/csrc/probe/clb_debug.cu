@@ -2,8 +2,8 @@
 // clb_debug_umma_mn: D[128x128] = A[128x32] * B[128x32]^T with A staged in shared memory in an MN-major (M contiguous)
 // 128B-swizzled layout -- probes which (atom order, LBO/SBO) convention the MN-major matrix descriptor expects, so that
 // NCHW activations (pixels contiguous) can be fed to the tensor core by TMA without a register transpose.
-#include "clb_tc_ptx.cuh"
-#include "clb_tc_loaders.cuh"
+#include "../clb_tc_ptx.cuh"
+#include "../clb_tc_loaders.cuh"
 
 namespace clb {
 namespace dbg {
@@ -189,7 +189,7 @@ extern "C" int clb_debug_umma_bf16(const float* A, const float* B, float* D, int
 
 // clb_debug_tma3d: one 3-D TMA box load (optionally 128B-swizzled) at arbitrary (possibly out-of-bounds) coordinates,
 // copied back verbatim from shared memory -- probes zero-fill / negative-coordinate behaviour and the swizzle pattern.
-#include "clb_tma.cuh"
+#include "../clb_tma.cuh"
 namespace clb {
 namespace dbg {
 __global__ void tma3d_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ out, int nfloats, int c0, int c1, int c2) {

@@ -229,12 +229,6 @@ int clb_nccl_init(const void* id128, int rank, int world, void** comm_out);
 int clb_nccl_allreduce_f32(void* comm, float* buf, int64_t n, void* stream);
 int clb_nccl_destroy(void* comm);
 
-/* diagnostic (bring-up of the MN-major shared-memory descriptor); not part of the hot path */
-int clb_debug_umma_mn(const float* At, const float* B, float* D, int variant, void* stream);
-int clb_debug_umma_bf16(const float* A, const float* B, float* D, int variant, void* stream);
-int clb_debug_tma3d(const float* x, int d0, int d1, int d2, int b0, int b1, int b2, int swizzle, int c0, int c1, int c2,
-                    float* out, void* stream);
-
 #ifdef __cplusplus
 }
 #endif

@@ -2,13 +2,28 @@
 import os, sys, subprocess
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+
+def _probe_lib():
+    """libclb_probe.so (clsurvey_b200/build.py build_probe): bring-up probes, not part of the product ABI."""
+    import ctypes
+    from clsurvey_b200 import build
+    lib = ctypes.CDLL(build.build_probe() if not os.path.exists(os.path.join(build.OUT_DIR, "libclb_probe.so")) else os.path.join(build.OUT_DIR, "libclb_probe.so"))
+    return lib
+
+
+def _probe_call(name, *args):
+    import ctypes
+    fn = getattr(_probe_lib(), name)
+    fn.restype = ctypes.c_int
+    rc = fn(*[ctypes.c_void_p(a) if isinstance(a, int) and a > 2 ** 31 else a for a in args])
+    assert rc == 0, (name, rc)
 from clsurvey_b200 import _capi
 _capi.lib()
 
 def one(W, H, P, box, coords, swz):
     x = torch.arange(W * H * P, dtype=torch.float32).reshape(P, H, W).cuda() + 1.0
     out = torch.full((box[0] * box[1] * box[2],), -7.0, device="cuda")
-    _capi.call("clb_debug_tma3d", x.data_ptr(), W, H, P, box[0], box[1], box[2], swz, coords[0], coords[1], coords[2],
+    _probe_call("clb_debug_tma3d", x.data_ptr(), W, H, P, box[0], box[1], box[2], swz, coords[0], coords[1], coords[2],
                out.data_ptr(), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     o = out.cpu().reshape(box[2], box[1], box[0])

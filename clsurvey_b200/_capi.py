@@ -40,7 +40,16 @@ SIGNATURES = {
     "clb_softmax_loss": [c_p, c_i, c_i, c_i, c_p, c_i, c_i, c_f, c_p, c_p, c_p, c_p],
     "clb_planes_conv_supported": [c_i] * 8,
     "clb_planes_weights": [c_p] * 5 + [c_i, c_i, c_p],
-    "clb_planes_weights_batch": [c_i] + [c_p] * 8,
+    "clb_planes_weights_batch": [c_i] + [c_p] * 9,
+    "clb_planes_linear_supported": [c_i, c_i],
+    "clb_planes_linear_fwd": [c_p] * 7 + [c_i] * 4 + [c_p],
+    "clb_planes_linear_dgrad": [c_p] * 7 + [c_i] * 3 + [c_p],
+    "clb_planes_linear_wgrad_ws": [c_i] * 3,
+    "clb_planes_linear_wgrad": [c_p] * 7 + [c_sz] + [c_i] * 4 + [c_p, c_f, c_f, c_p],
+    "clb_planes_pool_fwd_flat": [c_p] * 5 + [c_i] * 4 + [c_p],
+    "clb_planes_pool_bwd_flat": [c_p] * 6 + [c_i] * 4 + [c_p],
+    "clb_planes_to_f32": [c_p, c_p, c_p, c_i64, c_p],
+    "clb_planes_from_f32": [c_p, c_p, c_p, c_p, c_i64, c_p],
     "clb_planes_conv_fwd": [c_p] * 7 + [c_i] * 6 + [c_p],
     "clb_planes_conv_dgrad": [c_p] * 7 + [c_i] * 5 + [c_p],
     "clb_planes_conv_wgrad_ws": [c_i] * 5,
@@ -69,7 +78,7 @@ SIGNATURES = {
     "clb_nccl_allreduce_f32": [c_p, c_p, c_i64, c_p],
     "clb_nccl_destroy": [c_p],
 }
-_RESTYPE = {"clb_last_error": ctypes.c_char_p, "clb_conv2d_wgrad_ws": c_sz, "clb_planes_conv_wgrad_ws": c_sz, "clb_planes_conv1_ws": c_sz, "clb_launch_count": ctypes.c_ulonglong, "clb_linear_ws": c_sz}
+_RESTYPE = {"clb_last_error": ctypes.c_char_p, "clb_conv2d_wgrad_ws": c_sz, "clb_planes_conv_wgrad_ws": c_sz, "clb_planes_linear_wgrad_ws": c_sz, "clb_planes_conv1_ws": c_sz, "clb_launch_count": ctypes.c_ulonglong, "clb_linear_ws": c_sz}
 
 
 class ClbError(RuntimeError):

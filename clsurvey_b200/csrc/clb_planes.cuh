@@ -7,12 +7,14 @@ namespace pl {
 
 // clb_planes_conv.cu
 bool conv_supported(int C, int H, int W, int K, int R, int S, int stride, int pad);
+bool linear_supported(int in, int out);
+// taps = 9: 3x3 / pad 1 convolution; taps = 1: nn.Linear (H = W = 1, N = rows)
 int conv_fwd(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi, const uint16_t* w_lo, const float* bias, int relu,
-             const uint16_t* mask_hi, uint16_t* y_hi, uint16_t* y_lo, int N, int H, int W, int Cred, int Cout, cudaStream_t s);
-void wgrad_plan(int N, int H, int W, int Cred, int Cout, int* splits, int* kb_per_split, int* n_kb);
-size_t wgrad_ws_floats(int N, int H, int W, int Cred, int Cout);
+             const uint16_t* mask_hi, uint16_t* y_hi, uint16_t* y_lo, int N, int H, int W, int Cred, int Cout, int taps, cudaStream_t s);
+void wgrad_plan(int N, int H, int W, int Cred, int Cout, int taps, int* splits, int* kb_per_split, int* n_kb);
+size_t wgrad_ws_floats(int N, int H, int W, int Cred, int Cout, int taps);
 int conv_wgrad_partials(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* dy_hi, const uint16_t* dy_lo, float* ws,
-                        int* splits_out, int N, int H, int W, int Cred, int Cout, cudaStream_t s);
+                        int* splits_out, int N, int H, int W, int Cred, int Cout, int taps, cudaStream_t s);
 
 // bf16 helpers shared by the layer kernels
 __device__ __forceinline__ uint32_t bf16_bits_rn(float x) {          // round-to-nearest-even, like __float2bfloat16_rn

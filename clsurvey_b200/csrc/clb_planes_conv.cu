@@ -101,6 +101,7 @@ static TileGeom make_geom(int rows, int H, int W) {
 
 struct ConvArgs {
     int N, H, W, Cred, Cout;                             // Cred = reduction channels, Cout = output channels of the GEMM
+    int taps, pad;                                       // 9 / 1: 3x3 conv;  1 / 0: nn.Linear as a 1x1 'conv' on a 1x1 map (rows = samples)
     int n_items, n_tiles_n;                              // work items (persistent loop) and N tiles per M tile
     TileGeom tg;                                         // M tile (fwd / dgrad) or K block (wgrad) geometry
     // fwd / dgrad epilogue
@@ -152,7 +153,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 if (KIND == 0) {
                     const int nt = item % p.n_tiles_n, mt = item / p.n_tiles_n;
                     const int n0 = (mt / p.tg.tiles_h) * p.tg.bn, h0 = (mt % p.tg.tiles_h) * p.tg.bh;
-                    const int nkb = 9 * cpb;
+                    const int nkb = p.taps * cpb;
                     for (int kb = 0; kb < nkb; ++kb, ++it) {
                         const int s = it % kStages;
                         mbar_wait_wd(empty + 8 * s, ((it / kStages) & 1u) ^ 1u);
@@ -160,8 +161,8 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                         const int r = tap / 3, sx = tap - r * 3;
                         const uint32_t st = base + (uint32_t)s * kStageBytes;
                         tma::mbar_arrive_expect_tx(full + 8 * s, 2 * kABytes + 2 * kBBytes);
-                        tma::load_4d(st, &map_a_hi, full + 8 * s, cb * 64, sx - 1, h0 + r - 1, n0);
-                        tma::load_4d(st + kTileBytes, &map_a_lo, full + 8 * s, cb * 64, sx - 1, h0 + r - 1, n0);
+                        tma::load_4d(st, &map_a_hi, full + 8 * s, cb * 64, sx - p.pad, h0 + r - p.pad, n0);
+                        tma::load_4d(st + kTileBytes, &map_a_lo, full + 8 * s, cb * 64, sx - p.pad, h0 + r - p.pad, n0);
                         tma::load_2d(st + 2 * kTileBytes, &map_b_hi, full + 8 * s, kb * 64, nt * BN);
                         tma::load_2d(st + 3 * kTileBytes, &map_b_lo, full + 8 * s, kb * 64, nt * BN);
                     }
@@ -184,8 +185,8 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                         }
                         for (int j = 0; j < nblk; ++j) {              // X shifted by the tap of column block j
                             const int r = tap[j] / 3, sx = tap[j] - r * 3;
-                            tma::load_4d(st + 2 * kTileBytes + j * 8192, &map_b_hi, full + 8 * s, cb[j] * 64, sx - 1, h0 + r - 1, n0);
-                            tma::load_4d(st + 3 * kTileBytes + j * 8192, &map_b_lo, full + 8 * s, cb[j] * 64, sx - 1, h0 + r - 1, n0);
+                            tma::load_4d(st + 2 * kTileBytes + j * 8192, &map_b_hi, full + 8 * s, cb[j] * 64, sx - p.pad, h0 + r - p.pad, n0);
+                            tma::load_4d(st + 3 * kTileBytes + j * 8192, &map_b_lo, full + 8 * s, cb[j] * 64, sx - p.pad, h0 + r - p.pad, n0);
                         }
                     }
                 }
@@ -199,7 +200,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                 int nkb;
                 uint32_t idesc;
                 if (KIND == 0) {
-                    nkb = 9 * cpb;
+                    nkb = p.taps * cpb;
                     idesc = idesc_bf16(BN, false);
                 } else {
                     const int nt = (item / p.n_tiles_m) % p.n_tiles_n, z = item / (p.n_tiles_m * p.n_tiles_n);
@@ -259,7 +260,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         constexpr int kCols = BN / 2;                     // columns of this thread's half
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             int nkb;
-            if (KIND == 0) nkb = 9 * cpb;
+            if (KIND == 0) nkb = p.taps * cpb;
             else {
                 const int kb0 = (item / (p.n_tiles_m * p.n_tiles_n)) * p.kb_per_split;
                 nkb = min(kb0 + p.kb_per_split, p.n_kb_total) - kb0;
@@ -332,7 +333,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             } else {
                 const int mt = item % p.n_tiles_m, nt = (item / p.n_tiles_m) % p.n_tiles_n;
                 const int z = item / (p.n_tiles_m * p.n_tiles_n);
-                const int ld = p.ncb * 64;                            // 9 * Cred
+                const int ld = p.ncb * 64;                            // taps * Cred
                 const int kout = mt * 128 + row;
                 float* dst = p.ws + ((size_t)z * p.Cout + kout) * ld + (size_t)nt * 128 + half * 64;
                 const bool second = 2 * nt + 1 < p.ncb;
@@ -355,6 +356,9 @@ static int mn_swap() {                                  // bring-up switch (tool
     return v;
 }
 static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// nn.Linear(in, out) on the same kernel: a 1x1 "conv" over a 1x1 map whose 128-row tiles are 128 samples
+bool linear_supported(int in, int out) { return in >= 64 && (in % 64) == 0 && (out % 64) == 0; }
 
 bool conv_supported(int C, int H, int W, int K, int R, int S, int stride, int pad) {
     return R == 3 && S == 3 && stride == 1 && pad == 1 && (C % 64) == 0 && (K % 64) == 0 && pow2(H) && pow2(W) && W >= 4 &&
@@ -382,9 +386,10 @@ static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtens
 
 // y = conv3x3(x, w) [+ bias] [ReLU] [masked by mask_hi > 0], all planes NHWC.  w planes: [Cout][9][Cred] (K-major rows).
 int conv_fwd(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi, const uint16_t* w_lo, const float* bias, int relu,
-             const uint16_t* mask_hi, uint16_t* y_hi, uint16_t* y_lo, int N, int H, int W, int Cred, int Cout, cudaStream_t s) {
+             const uint16_t* mask_hi, uint16_t* y_hi, uint16_t* y_lo, int N, int H, int W, int Cred, int Cout, int taps, cudaStream_t s) {
     ConvArgs p{};
     p.N = N; p.H = H; p.W = W; p.Cred = Cred; p.Cout = Cout;
+    p.taps = taps; p.pad = taps == 9 ? 1 : 0;
     p.tg = make_geom(128, H, W);
     const int bn_tile = (Cout % 128 == 0) ? 128 : 64;
     p.n_tiles_n = Cout / bn_tile;
@@ -395,8 +400,8 @@ int conv_fwd(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi, c
     int rc;
     if ((rc = encode_act(&a_hi, x_hi, N, H, W, Cred, p.tg.bh, p.tg.bn))) return rc;
     if ((rc = encode_act(&a_lo, x_lo, N, H, W, Cred, p.tg.bh, p.tg.bn))) return rc;
-    const uint64_t dims[2] = {(uint64_t)9 * Cred, (uint64_t)Cout};
-    const uint64_t str[1] = {(uint64_t)9 * Cred * 2};
+    const uint64_t dims[2] = {(uint64_t)taps * Cred, (uint64_t)Cout};
+    const uint64_t str[1] = {(uint64_t)taps * Cred * 2};
     const uint32_t box[2] = {64u, (uint32_t)bn_tile};
     if ((rc = tma::encode_bf16(&b_hi, w_hi, 2, dims, str, box, true))) return rc;
     if ((rc = tma::encode_bf16(&b_lo, w_lo, 2, dims, str, box, true))) return rc;
@@ -407,10 +412,10 @@ int conv_fwd(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi, c
 // persistent CTA then does exactly one equally long work item -- no tail round -- and the partial-sum workspace is as small as
 // the parallelism allows: 1 split, i.e. no reduction traffic at all, for the 144-tile layers).  Fixed 148 => the summation
 // order, and with it every bit of dW, does not depend on the device it runs on.
-void wgrad_plan(int N, int H, int W, int Cred, int Cout, int* splits, int* kb_per_split, int* n_kb) {
+void wgrad_plan(int N, int H, int W, int Cred, int Cout, int taps, int* splits, int* kb_per_split, int* n_kb) {
     const TileGeom g = make_geom(64, H, W);
     const int nkb = ((N + g.bn - 1) / g.bn) * g.tiles_h;
-    const int tiles = ((Cout + 127) / 128) * ((9 * (Cred / 64) + 1) / 2);
+    const int tiles = ((Cout + 127) / 128) * ((taps * (Cred / 64) + 1) / 2);
     int want = 148 / tiles;
     if (want > nkb) want = nkb;
     if (want < 1) want = 1;
@@ -419,20 +424,21 @@ void wgrad_plan(int N, int H, int W, int Cred, int Cout, int* splits, int* kb_pe
     *splits = (nkb + per - 1) / per;
     *n_kb = nkb;
 }
-size_t wgrad_ws_floats(int N, int H, int W, int Cred, int Cout) {
+size_t wgrad_ws_floats(int N, int H, int W, int Cred, int Cout, int taps) {
     int splits, per, nkb;
-    wgrad_plan(N, H, W, Cred, Cout, &splits, &per, &nkb);
-    return (size_t)splits * Cout * 9 * Cred;
+    wgrad_plan(N, H, W, Cred, Cout, taps, &splits, &per, &nkb);
+    return (size_t)splits * Cout * taps * Cred;
 }
 
 // ws[z][Cout][9][Cred] = partial sums of dY^T X_tap over the pixel range of split z
 int conv_wgrad_partials(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* dy_hi, const uint16_t* dy_lo, float* ws,
-                        int* splits_out, int N, int H, int W, int Cred, int Cout, cudaStream_t s) {
+                        int* splits_out, int N, int H, int W, int Cred, int Cout, int taps, cudaStream_t s) {
     ConvArgs p{};
     p.N = N; p.H = H; p.W = W; p.Cred = Cred; p.Cout = Cout;
+    p.taps = taps; p.pad = taps == 9 ? 1 : 0;
     p.tg = make_geom(64, H, W);
-    wgrad_plan(N, H, W, Cred, Cout, &p.splits, &p.kb_per_split, &p.n_kb_total);
-    p.ncb = 9 * (Cred / 64);
+    wgrad_plan(N, H, W, Cred, Cout, taps, &p.splits, &p.kb_per_split, &p.n_kb_total);
+    p.ncb = taps * (Cred / 64);
     p.n_tiles_m = (Cout + 127) / 128;
     p.n_tiles_n = (p.ncb + 1) / 2;
     p.n_items = p.n_tiles_m * p.n_tiles_n * p.splits;

@@ -19,32 +19,31 @@ static inline int ew_grid(int64_t n, int threads) {
 // transposed channels), each as bf16 hi / lo planes.  blockIdx.y selects the layout so that the writes of both are coalesced.
 __global__ void __launch_bounds__(256) weights_to_planes_kernel(const float* __restrict__ w, uint16_t* __restrict__ wf_hi,
                                                                 uint16_t* __restrict__ wf_lo, uint16_t* __restrict__ wt_hi,
-                                                                uint16_t* __restrict__ wt_lo, int K, int C) {
+                                                                uint16_t* __restrict__ wt_lo, int K, int C, int taps) {
     const int64_t total = (int64_t)K * C, gs = (int64_t)gridDim.x * blockDim.x;
     const bool dgrad = blockIdx.y == 1;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gs) {
         int k, c;
         if (!dgrad) { k = (int)(i / C); c = (int)(i - (int64_t)k * C); }          // c fastest
         else { c = (int)(i / K); k = (int)(i - (int64_t)c * K); }                  // k fastest
-        const float* src = w + ((int64_t)k * C + c) * 9;
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
+        const float* src = w + ((int64_t)k * C + c) * taps;
+        for (int t = 0; t < taps; ++t) {
             uint32_t hi, lo;
             split1(__ldg(src + t), hi, lo);
             if (!dgrad) {
-                const int64_t o = ((int64_t)k * 9 + t) * C + c;
+                const int64_t o = ((int64_t)k * taps + t) * C + c;
                 wf_hi[o] = (uint16_t)hi; wf_lo[o] = (uint16_t)lo;
             } else {
-                const int64_t o = ((int64_t)c * 9 + (8 - t)) * K + k;
+                const int64_t o = ((int64_t)c * taps + (taps - 1 - t)) * K + k;
                 wt_hi[o] = (uint16_t)hi; wt_lo[o] = (uint16_t)lo;
             }
         }
     }
 }
-int weights_to_planes(const float* w, uint16_t* wf_hi, uint16_t* wf_lo, uint16_t* wt_hi, uint16_t* wt_lo, int K, int C,
+int weights_to_planes(const float* w, uint16_t* wf_hi, uint16_t* wf_lo, uint16_t* wt_hi, uint16_t* wt_lo, int K, int C, int taps,
                       cudaStream_t s) {
     dim3 grid(ew_grid((int64_t)K * C, 256), wt_hi ? 2 : 1);
-    weights_to_planes_kernel<<<grid, 256, 0, s>>>(w, wf_hi, wf_lo, wt_hi, wt_lo, K, C); clb::count_launch();
+    weights_to_planes_kernel<<<grid, 256, 0, s>>>(w, wf_hi, wf_lo, wt_hi, wt_lo, K, C, taps); clb::count_launch();
     return CLB_OK;
 }
 
@@ -55,14 +54,14 @@ struct WeightBatch {
     int n;
     const float* w[kMax];
     uint16_t *wf_hi[kMax], *wf_lo[kMax], *wt_hi[kMax], *wt_lo[kMax];
-    int K[kMax], C[kMax];
+    int K[kMax], C[kMax], taps[kMax];                // taps = 9 (3x3 conv weight [K][C][3][3]) or 1 (nn.Linear weight [K][C])
 };
 __global__ void __launch_bounds__(256) weights_to_planes_batch_kernel(const __grid_constant__ WeightBatch b) {
     // thread = two adjacent elements of the contiguous output dimension (c for the forward layout, k for the dgrad layout):
     // 4-byte stores, coalesced along that dimension; C and K are multiples of 64
     const int layer = blockIdx.y >> 1;
     const bool dgrad = blockIdx.y & 1;
-    const int K = b.K[layer], C = b.C[layer];
+    const int K = b.K[layer], C = b.C[layer], taps = b.taps[layer];
     const float* __restrict__ w = b.w[layer];
     uint32_t* __restrict__ o_hi = reinterpret_cast<uint32_t*>(dgrad ? b.wt_hi[layer] : b.wf_hi[layer]);
     uint32_t* __restrict__ o_lo = reinterpret_cast<uint32_t*>(dgrad ? b.wt_lo[layer] : b.wf_lo[layer]);
@@ -72,30 +71,29 @@ __global__ void __launch_bounds__(256) weights_to_planes_batch_kernel(const __gr
         const float *s0, *s1;
         if (!dgrad) {
             k = (int)(i / (C / 2)); c = 2 * (int)(i - (int64_t)k * (C / 2));
-            s0 = w + ((int64_t)k * C + c) * 9; s1 = s0 + 9;
+            s0 = w + ((int64_t)k * C + c) * taps; s1 = s0 + taps;
         } else {
             c = (int)(i / (K / 2)); k = 2 * (int)(i - (int64_t)c * (K / 2));
-            s0 = w + ((int64_t)k * C + c) * 9; s1 = s0 + (int64_t)C * 9;
+            s0 = w + ((int64_t)k * C + c) * taps; s1 = s0 + (int64_t)C * taps;
         }
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
+        for (int t = 0; t < taps; ++t) {
             uint32_t h0, l0, h1, l1;
             split1(__ldg(s0 + t), h0, l0);
             split1(__ldg(s1 + t), h1, l1);
-            const int64_t o = dgrad ? (((int64_t)c * 9 + (8 - t)) * K + k) >> 1 : (((int64_t)k * 9 + t) * C + c) >> 1;
+            const int64_t o = dgrad ? (((int64_t)c * taps + (taps - 1 - t)) * K + k) >> 1 : (((int64_t)k * taps + t) * C + c) >> 1;
             o_hi[o] = h0 | (h1 << 16); o_lo[o] = l0 | (l1 << 16);
         }
     }
 }
 int weights_to_planes_batch(int n, const float* const* w, void* const* wf_hi, void* const* wf_lo, void* const* wt_hi, void* const* wt_lo,
-                            const int* K, const int* C, cudaStream_t s) {
+                            const int* K, const int* C, const int* taps, cudaStream_t s) {
     WeightBatch b;
     b.n = n;
     int64_t mx = 1;
     for (int i = 0; i < n; ++i) {
         b.w[i] = w[i]; b.wf_hi[i] = (uint16_t*)wf_hi[i]; b.wf_lo[i] = (uint16_t*)wf_lo[i];
         b.wt_hi[i] = (uint16_t*)wt_hi[i]; b.wt_lo[i] = (uint16_t*)wt_lo[i];
-        b.K[i] = K[i]; b.C[i] = C[i];
+        b.K[i] = K[i]; b.C[i] = C[i]; b.taps[i] = taps ? taps[i] : 9;
         if ((int64_t)K[i] * C[i] > mx) mx = (int64_t)K[i] * C[i];
     }
     int gx = (int)((mx / 2 + 255) / 256);
@@ -110,7 +108,8 @@ struct U8x8 { uint32_t a, b; };
 
 // planes [N][H][W][C] -> planes [N][H/2][W/2][C] (OUT_NCHW: fp32 [N][C][H/2][W/2], the classifier's flatten order) + argmax
 // [N][H/2][W/2][C] u8.  One thread = 8 channels of one output pixel.
-template <bool OUT_NCHW>
+// OUT: 0 = planes NHWC, 1 = fp32 [N][C][PH][PW], 2 = planes in that same flatten order (input of a planes nn.Linear)
+template <int OUT>
 __global__ void __launch_bounds__(256) pool_planes_fwd_kernel(const uint16_t* __restrict__ x_hi, const uint16_t* __restrict__ x_lo,
                                                               uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo,
                                                               float* __restrict__ y_f32, uint8_t* __restrict__ am, int N, int H,
@@ -139,9 +138,15 @@ __global__ void __launch_bounds__(256) pool_planes_fwd_kernel(const uint16_t* __
             }
         }
         const int64_t o = op * C + c8 * 8;
-        if (OUT_NCHW) {
+        if (OUT == 1) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) y_f32[(((int64_t)n * C + c8 * 8 + j) * PH + ph) * PW + pw] = best[j];
+        } else if (OUT == 2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int64_t q = (((int64_t)n * C + c8 * 8 + j) * PH + ph) * PW + pw;
+                y_hi[q] = (uint16_t)bh[j]; y_lo[q] = (uint16_t)bl[j];
+            }
         } else {
             *reinterpret_cast<uint4*>(y_hi + o) = make_uint4(bh[0] | (bh[1] << 16), bh[2] | (bh[3] << 16), bh[4] | (bh[5] << 16), bh[6] | (bh[7] << 16));
             *reinterpret_cast<uint4*>(y_lo + o) = make_uint4(bl[0] | (bl[1] << 16), bl[2] | (bl[3] << 16), bl[4] | (bl[5] << 16), bl[6] | (bl[7] << 16));
@@ -186,8 +191,8 @@ __global__ void __launch_bounds__(256) pool_nchw_to_planes_kernel(const float* _
 
 // backward, planes out: dx[n][2ph+r][2pw+s][c] = (argmax == 2r+s && pooled > 0) ? dy[n][ph][pw][c] : 0   (max-pool backward
 // fused with the ReLU mask of the conv in front: pooled > 0 <=> the selected pre-pool activation was > 0).
-// IN_NCHW: dy and the pooled activation are fp32 [N][C][PH][PW] (classifier side), else planes.
-template <bool IN_NCHW>
+// IN: 0 = dy / pooled as planes NHWC, 1 = fp32 [N][C][PH][PW] (classifier side), 2 = planes in that flatten order.
+template <int IN>
 __global__ void __launch_bounds__(256) pool_planes_bwd_kernel(const uint16_t* __restrict__ dy_hi, const uint16_t* __restrict__ dy_lo,
                                                               const float* __restrict__ dy_f32, const uint16_t* __restrict__ pooled_hi,
                                                               const float* __restrict__ pooled_f32, const uint8_t* __restrict__ am,
@@ -204,12 +209,21 @@ __global__ void __launch_bounds__(256) pool_planes_bwd_kernel(const uint16_t* __
         const uint2 a = __ldg(reinterpret_cast<const uint2*>(am + o));
 #pragma unroll
         for (int j = 0; j < 8; ++j) idx[j] = ((j < 4 ? a.x : a.y) >> (8 * (j & 3))) & 0xFFu;
-        if (IN_NCHW) {
+        if (IN == 1) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int64_t q = (((int64_t)n * C + c8 * 8 + j) * PH + ph) * PW + pw;
                 const float g = __ldg(pooled_f32 + q) > 0.f ? __ldg(dy_f32 + q) : 0.f;
                 split1(g, gh[j], gl[j]);
+            }
+        } else if (IN == 2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int64_t q = (((int64_t)n * C + c8 * 8 + j) * PH + ph) * PW + pw;
+                const uint32_t mb = pooled_hi[q];
+                const bool on = mb != 0 && mb < 0x8000u;
+                gh[j] = on ? dy_hi[q] : 0u;
+                gl[j] = on ? dy_lo[q] : 0u;
             }
         } else {
             const uint4 h = __ldg(reinterpret_cast<const uint4*>(dy_hi + o)), l = __ldg(reinterpret_cast<const uint4*>(dy_lo + o));
@@ -260,10 +274,11 @@ __global__ void __launch_bounds__(256) pool_planes_bwd_to_nchw_kernel(const uint
 }
 
 int pool_fwd(const uint16_t* x_hi, const uint16_t* x_lo, uint16_t* y_hi, uint16_t* y_lo, float* y_f32, uint8_t* am, int N, int H,
-             int W, int C, cudaStream_t s) {
+             int W, int C, int flat, cudaStream_t s) {
     const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
-    if (y_f32) pool_planes_fwd_kernel<true><<<ew_grid(total, 256), 256, 0, s>>>(x_hi, x_lo, nullptr, nullptr, y_f32, am, N, H, W, C);
-    else pool_planes_fwd_kernel<false><<<ew_grid(total, 256), 256, 0, s>>>(x_hi, x_lo, y_hi, y_lo, nullptr, am, N, H, W, C);
+    if (y_f32) pool_planes_fwd_kernel<1><<<ew_grid(total, 256), 256, 0, s>>>(x_hi, x_lo, nullptr, nullptr, y_f32, am, N, H, W, C);
+    else if (flat) pool_planes_fwd_kernel<2><<<ew_grid(total, 256), 256, 0, s>>>(x_hi, x_lo, y_hi, y_lo, nullptr, am, N, H, W, C);
+    else pool_planes_fwd_kernel<0><<<ew_grid(total, 256), 256, 0, s>>>(x_hi, x_lo, y_hi, y_lo, nullptr, am, N, H, W, C);
     clb::count_launch();
     return CLB_OK;
 }
@@ -273,11 +288,40 @@ int pool_fwd_from_nchw(const float* x, uint16_t* y_hi, uint16_t* y_lo, uint8_t* 
     return CLB_OK;
 }
 int pool_bwd(const uint16_t* dy_hi, const uint16_t* dy_lo, const float* dy_f32, const uint16_t* pooled_hi, const float* pooled_f32,
-             const uint8_t* am, uint16_t* dx_hi, uint16_t* dx_lo, int N, int H, int W, int C, cudaStream_t s) {
+             const uint8_t* am, uint16_t* dx_hi, uint16_t* dx_lo, int N, int H, int W, int C, int flat, cudaStream_t s) {
     const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
-    if (dy_f32) pool_planes_bwd_kernel<true><<<ew_grid(total, 256), 256, 0, s>>>(nullptr, nullptr, dy_f32, nullptr, pooled_f32, am, dx_hi, dx_lo, N, H, W, C);
-    else pool_planes_bwd_kernel<false><<<ew_grid(total, 256), 256, 0, s>>>(dy_hi, dy_lo, nullptr, pooled_hi, nullptr, am, dx_hi, dx_lo, N, H, W, C);
+    if (dy_f32) pool_planes_bwd_kernel<1><<<ew_grid(total, 256), 256, 0, s>>>(nullptr, nullptr, dy_f32, nullptr, pooled_f32, am, dx_hi, dx_lo, N, H, W, C);
+    else if (flat) pool_planes_bwd_kernel<2><<<ew_grid(total, 256), 256, 0, s>>>(dy_hi, dy_lo, nullptr, pooled_hi, nullptr, am, dx_hi, dx_lo, N, H, W, C);
+    else pool_planes_bwd_kernel<0><<<ew_grid(total, 256), 256, 0, s>>>(dy_hi, dy_lo, nullptr, pooled_hi, nullptr, am, dx_hi, dx_lo, N, H, W, C);
     clb::count_launch();
+    return CLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ fp32 <-> planes
+__global__ void __launch_bounds__(256) planes_to_f32_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo,
+                                                            float* __restrict__ out, int64_t n) {
+    const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) out[i] = join1(hi[i], lo[i]);
+}
+// hi/lo planes of x, zeroed where mask_hi (a post-ReLU activation's hi plane, may be NULL) is <= 0: the ReLU backward of a
+// planes nn.Linear applied to the fp32 gradient that arrives from a layer outside the planes pipeline
+__global__ void __launch_bounds__(256) f32_to_planes_kernel(const float* __restrict__ x, const uint16_t* __restrict__ mask_hi,
+                                                            uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t n) {
+    const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
+        float v = x[i];
+        if (mask_hi) { const uint32_t mb = mask_hi[i]; if (!(mb != 0 && mb < 0x8000u)) v = 0.f; }
+        uint32_t h, l;
+        split1(v, h, l);
+        hi[i] = (uint16_t)h; lo[i] = (uint16_t)l;
+    }
+}
+int planes_to_f32(const uint16_t* hi, const uint16_t* lo, float* out, int64_t n, cudaStream_t s) {
+    planes_to_f32_kernel<<<ew_grid(n, 256), 256, 0, s>>>(hi, lo, out, n); clb::count_launch();
+    return CLB_OK;
+}
+int f32_to_planes(const float* x, const uint16_t* mask_hi, uint16_t* hi, uint16_t* lo, int64_t n, cudaStream_t s) {
+    f32_to_planes_kernel<<<ew_grid(n, 256), 256, 0, s>>>(x, mask_hi, hi, lo, n); clb::count_launch();
     return CLB_OK;
 }
 int pool_bwd_to_nchw(const uint16_t* dy_hi, const uint16_t* dy_lo, const uint16_t* pooled_hi, const uint8_t* am, float* dx, int N,
@@ -293,37 +337,44 @@ int pool_bwd_to_nchw(const uint16_t* dy_hi, const uint16_t* dy_lo, const uint16_
 constexpr int kBiasChunks = 592;
 __global__ void __launch_bounds__(256) bias_partials_kernel(const uint16_t* __restrict__ dy_hi, const uint16_t* __restrict__ dy_lo,
                                                             float* __restrict__ part, int64_t npix, int K, int64_t pix_per_chunk) {
-    // thread = 8 channels (one 16-byte load per plane) of every `rows`-th pixel of the chunk; K <= 2048
+    // thread = 8 channels (one 16-byte load per plane) of every `rows`-th pixel of the chunk; channel groups beyond the CTA's
+    // 256 threads are handled in further passes
     const int K8 = K >> 3;
-    const int rows = 256 / K8;                                      // pixel rows in flight (K8 <= 256)
-    const int sub = threadIdx.x / K8, c8 = threadIdx.x - sub * K8;
+    const int tpr = K8 < 256 ? K8 : 256;                            // threads per pixel row
+    const int rows = 256 / tpr;                                     // pixel rows in flight
+    const int sub = threadIdx.x / tpr, lc = threadIdx.x - sub * tpr;
     const int64_t p0 = (int64_t)blockIdx.x * pix_per_chunk, p1 = min(npix, p0 + pix_per_chunk);
-    float acc[8];
+    __shared__ float red[256 * 9];
+    for (int c0 = 0; c0 < K8; c0 += tpr) {                          // same trip count for every thread
+        const int c8 = c0 + lc;
+        float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    if (sub < rows) {
-        const uint4* hp = reinterpret_cast<const uint4*>(dy_hi) + c8;
-        const uint4* lp = reinterpret_cast<const uint4*>(dy_lo) + c8;
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        if (sub < rows && c8 < K8) {
+            const uint4* hp = reinterpret_cast<const uint4*>(dy_hi) + c8;
+            const uint4* lp = reinterpret_cast<const uint4*>(dy_lo) + c8;
 #pragma unroll 4
-        for (int64_t p = p0 + sub; p < p1; p += rows) {
-            const uint4 h = __ldg(hp + p * K8), l = __ldg(lp + p * K8);
-            const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+            for (int64_t p = p0 + sub; p < p1; p += rows) {
+                const uint4 h = __ldg(hp + p * K8), l = __ldg(lp + p * K8);
+                const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                acc[2 * j] += __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
-                acc[2 * j + 1] += __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
+                for (int j = 0; j < 4; ++j) {
+                    acc[2 * j] += __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+                    acc[2 * j + 1] += __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lw[j] & 0xFFFF0000u);
+                }
             }
         }
-    }
-    __shared__ float red[256 * 9];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) red[threadIdx.x * 9 + j] = acc[j];
-    __syncthreads();
-    for (int i = threadIdx.x; i < K; i += 256) {                    // fixed-order sum over the rows
-        const int cc8 = i >> 3, j = i & 7;
-        float s = 0.f;
-        for (int r = 0; r < rows; ++r) s += red[(r * K8 + cc8) * 9 + j];
-        part[(int64_t)blockIdx.x * K + i] = s;
+        for (int j = 0; j < 8; ++j) red[threadIdx.x * 9 + j] = acc[j];
+        __syncthreads();
+        const int kc = (tpr * 8 < K - c0 * 8) ? tpr * 8 : K - c0 * 8;      // channels of this pass
+        for (int i = threadIdx.x; i < kc; i += 256) {                    // fixed-order sum over the rows
+            const int cc8 = i >> 3, j = i & 7;
+            float s = 0.f;
+            for (int r = 0; r < rows; ++r) s += red[(r * tpr + cc8) * 9 + j];
+            part[(int64_t)blockIdx.x * K + c0 * 8 + i] = s;
+        }
+        __syncthreads();
     }
 }
 // one warp per channel: lane l adds chunks l, l + 32, ... in order, then a fixed xor-shuffle tree (deterministic)
@@ -349,20 +400,21 @@ int bias_grad(const uint16_t* dy_hi, const uint16_t* dy_lo, float* db, float* pa
 // by the importance update of the reference's passes over the batch gradient (J-1: "fused into the backward pass"):
 //   imp_mode 1 (EWC, main_EWC.py:151-156):  omega += dw * dw / imp_a
 //   imp_mode 2 (MAS, train_MAS.py:163-177): omega = (omega * imp_a + |dw|) / imp_b
+template <int TAPS>
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, float* __restrict__ omega,
                                                            int K, int C, int splits, int imp_mode, float imp_a, float imp_b) {
     // warp = 32 consecutive channels of one filter k: reads are coalesced along c (ws is [z][k][tap][c]), the 288 results are
     // transposed through shared memory and written as one contiguous run of dw[k][c0..c0+31][9]
-    __shared__ float buf[8][288];
+    __shared__ float buf[8][32 * TAPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t total = (int64_t)K * C * 9;
+    const int64_t total = (int64_t)K * C * TAPS;
     const int cg = C >> 5;                                           // C % 64 == 0
     const int64_t n_groups = (int64_t)K * cg;
     for (int64_t g = (int64_t)blockIdx.x * 8 + warp; g < n_groups; g += (int64_t)gridDim.x * 8) {
         const int k = (int)(g / cg), c0 = (int)(g - (int64_t)k * cg) * 32;
-        const float* src = ws + ((int64_t)k * 9) * C + c0 + lane;
+        const float* src = ws + ((int64_t)k * TAPS) * C + c0 + lane;
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {                 // four interleaved partial sums: loads in flight, order still fixed
+        for (int t = 0; t < TAPS; ++t) {                 // four interleaved partial sums: loads in flight, order still fixed
             const float* q = src + (int64_t)t * C;
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
             int z = 0;
@@ -371,12 +423,12 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
                 a2 += q[(int64_t)(z + 2) * total]; a3 += q[(int64_t)(z + 3) * total];
             }
             for (; z < splits; ++z) a0 += q[(int64_t)z * total];
-            buf[warp][lane * 9 + t] = (a0 + a1) + (a2 + a3);
+            buf[warp][lane * TAPS + t] = (a0 + a1) + (a2 + a3);
         }
         __syncwarp();
-        const int64_t o0 = ((int64_t)k * C + c0) * 9;
+        const int64_t o0 = ((int64_t)k * C + c0) * TAPS;
 #pragma unroll
-        for (int it = 0; it < 9; ++it) {
+        for (int it = 0; it < TAPS; ++it) {
             const float s = buf[warp][it * 32 + lane];
             const int64_t o = o0 + it * 32 + lane;
             dw[o] = s;
@@ -386,9 +438,11 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
         __syncwarp();
     }
 }
-int wgrad_reduce(const float* ws, float* dw, float* omega, int K, int C, int splits, int imp_mode, float imp_a, float imp_b,
+int wgrad_reduce(const float* ws, float* dw, float* omega, int K, int C, int taps, int splits, int imp_mode, float imp_a, float imp_b,
                  cudaStream_t s) {
-    wgrad_reduce_kernel<<<ew_grid((int64_t)K * C, 32), 256, 0, s>>>(ws, dw, omega, K, C, splits, imp_mode, imp_a, imp_b); clb::count_launch();
+    if (taps == 9) wgrad_reduce_kernel<9><<<ew_grid((int64_t)K * C, 32), 256, 0, s>>>(ws, dw, omega, K, C, splits, imp_mode, imp_a, imp_b);
+    else wgrad_reduce_kernel<1><<<ew_grid((int64_t)K * C, 32), 256, 0, s>>>(ws, dw, omega, K, C, splits, imp_mode, imp_a, imp_b);
+    clb::count_launch();
     return CLB_OK;
 }
 

@@ -243,6 +243,8 @@ class Engine:
                 max_act = max(max_act, n)
             elif not op.get("transient"):                 # bf16 hi / lo planes, NHWC (csrc/clb_planes_conv.cu)
                 op["out_pl"] = torch.empty(2, B * n, dtype=torch.int16, device=self.device)
+                if op.get("also_f32"):
+                    op["out"] = torch.empty(B * n, dtype=torch.float32, device=self.device)
             if op["kind"] == "maxpool":
                 op["argmax"] = torch.empty(B * n, dtype=torch.uint8, device=self.device)
         in_numel = self.input_shape[0] * self.input_shape[1] * self.input_shape[2]
@@ -250,7 +252,8 @@ class Engine:
         self.dbuf = [torch.empty(B * max_act, dtype=torch.float32, device=self.device) for _ in range(2)]
         self.dlogits = torch.empty(B * self.n_outputs, dtype=torch.float32, device=self.device)
         ws_bytes, wt_elems = 16, 4
-        pl_max = max([op["out_numel"] for op in ops if op.get("lay_out") == "planes"] +
+        pl_max = max([op["out_numel"] for op in ops if op.get("lay_out") in ("planes", "planes_flat")] +
+                     [op["inf"] for op in ops if op["kind"] == "linear" and op.get("planes")] +
                      [op["C"] * op["H"] * op["W"] for op in ops if op["kind"] == "conv" and op.get("planes")] + [0])
         self.pl_scratch = self.dpl = None
         if pl_max:
@@ -271,12 +274,16 @@ class Engine:
         if any(op.get("fused_first") for op in ops):
             ws_bytes = max(ws_bytes, _capi.lib().clb_planes_conv1_ws())
         for op in ops:
-            if op["kind"] == "linear":
+            if op["kind"] == "linear" and op.get("planes"):
+                op["wf"] = torch.empty(2, op["outf"] * op["inf"], dtype=torch.int16, device=self.device)    # [out][in] hi / lo
+                op["wt"] = torch.empty(2, op["outf"] * op["inf"], dtype=torch.int16, device=self.device)    # [in][out] hi / lo
+                ws_bytes = max(ws_bytes, _capi.lib().clb_planes_linear_wgrad_ws(B, op["inf"], op["outf"]))
+            elif op["kind"] == "linear":
                 ws_bytes = max(ws_bytes, _capi.lib().clb_linear_ws(B, op["inf"], op["outf"]))
         # importance passes (EWC Fisher / MAS omega) fuse `omega (+)= f(dW)` into the split-K reduction of the planes convs
         # (clb_planes_conv_wgrad, imp_mode); the flat-buffer ranges NOT covered by those weights get the streaming kernel
         covered = sorted((self.offsets[op["w"]], self.offsets[op["w"]] + (self.numels[op["w"]] + 3) // 4 * 4)
-                         for op in ops if op["kind"] == "conv" and op.get("planes"))
+                         for op in ops if op["kind"] in ("conv", "linear") and op.get("planes"))
         self._imp_rest, pos = [], 0
         for a, b in covered:
             if a > pos:
@@ -285,14 +292,16 @@ class Engine:
         if pos < self.total:
             self._imp_rest.append((pos, self.total - pos))
         self._wbatch = None
-        pconvs = [op for op in ops if op["kind"] == "conv" and op.get("planes")]
+        pconvs = [op for op in ops if op["kind"] in ("conv", "linear") and op.get("planes")]
         if pconvs:
             n = len(pconvs)
             P, I = ctypes.c_void_p * n, ctypes.c_int * n
+            lin = lambda op: op["kind"] == "linear"
             self._wbatch = (n, P(*[_ptr(self.view(self.theta, op["w"])) for op in pconvs]),
                             P(*[_ptr(op["wf"][0]) for op in pconvs]), P(*[_ptr(op["wf"][1]) for op in pconvs]),
                             P(*[_ptr(op["wt"][0]) for op in pconvs]), P(*[_ptr(op["wt"][1]) for op in pconvs]),
-                            I(*[op["K"] for op in pconvs]), I(*[op["C"] for op in pconvs]))
+                            I(*[op["outf"] if lin(op) else op["K"] for op in pconvs]),
+                            I(*[op["inf"] if lin(op) else op["C"] for op in pconvs]), I(*[1 if lin(op) else 9 for op in pconvs]))
         self.ws = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=self.device)
         self.wt_ws = torch.empty(wt_elems, dtype=torch.float32, device=self.device)
         self.loss_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
@@ -351,6 +360,24 @@ class Engine:
                         and lib.clb_planes_conv1_supported(prev["C"], prev["H"], prev["W"], prev["K"], prev["R"], prev["S"],
                                                            prev["stride"], prev["pad"])):
                     prev["fused_first"] = op["fused_prev"] = True
+        # classifier: nn.Linear + ReLU layers on the planes kernels (a 1x1 "conv" over a 1x1 map, rows = samples) when the
+        # features end in a planes pool, no Dropout sits in the classifier (VGG) and in % 64 == out % 64 == 0.  The pool
+        # then emits planes in the flatten order; the last planes Linear also leaves an fp32 copy for the head.
+        cls_ops = ops[nfeat:]
+        last_feat = ops[nfeat - 1] if nfeat > 0 else None
+        if (os.environ.get("CLB_PLANES_LINEAR", "1") != "0" and last_feat is not None and last_feat["kind"] == "maxpool"
+                and last_feat.get("lay_in") == "planes" and cls_ops and all(o["kind"] == "linear" for o in cls_ops)):
+            chain = True
+            for j, o in enumerate(cls_ops):
+                o["planes"] = bool(chain and o["relu"] and o["b"] is not None and j + 1 < len(cls_ops)
+                                   and lib.clb_planes_linear_supported(o["inf"], o["outf"]))
+                chain = o["planes"]
+            if cls_ops[0]["planes"]:
+                last_feat["lay_out"] = "planes_flat"
+            for j, o in enumerate(cls_ops):
+                if o["planes"]:
+                    o["lay_out"] = "planes"
+                    o["also_f32"] = not cls_ops[j + 1].get("planes")      # the legacy layer behind reads fp32
 
     # ------------------------------------------------------------------ forward
     def forward(self, x, train=False, masks=None):
@@ -402,6 +429,11 @@ class Engine:
                     call("clb_planes_pool_fwd", _ptr(cur[0]), _ptr(cur[1]), _ptr(out[0]), _ptr(out[1]), 0, _ptr(op["argmax"]),
                          n, op["H"], op["W"], op["C"], s)
                     cur = out
+                elif op["lay_out"] == "planes_flat":                  # planes in the classifier's flatten order
+                    out = op["out_pl"]
+                    call("clb_planes_pool_fwd_flat", _ptr(cur[0]), _ptr(cur[1]), _ptr(out[0]), _ptr(out[1]), _ptr(op["argmax"]),
+                         n, op["H"], op["W"], op["C"], s)
+                    cur = out
                 else:                                                 # planes -> fp32 NCHW (classifier / legacy consumer)
                     call("clb_planes_pool_fwd", _ptr(cur[0]), _ptr(cur[1]), 0, 0, _ptr(op["out"]), _ptr(op["argmax"]), n,
                          op["H"], op["W"], op["C"], s)
@@ -420,6 +452,14 @@ class Engine:
                 call("clb_adaptive_avgpool_fwd", _ptr(cur), _ptr(op["out"]), n, op["C"], op["H"], op["W"], op["OH"],
                      op["OW"], s)
                 cur = op["out"]
+            elif k == "linear" and op.get("planes"):
+                out = op["out_pl"]
+                self._timed(call, "clb_planes_linear_fwd", _ptr(cur[0]), _ptr(cur[1]), _ptr(op["wf"][0]), _ptr(op["wf"][1]),
+                            _ptr(self.view(self.theta, op["b"])), _ptr(out[0]), _ptr(out[1]), n, op["inf"], op["outf"], 1, s)
+                cur = out
+                if op["also_f32"]:                                    # the head (not a multiple of 64 wide) runs on fp32
+                    call("clb_planes_to_f32", _ptr(out[0]), _ptr(out[1]), _ptr(op["out"]), n * op["outf"], s)
+                    cur = op["out"]
             elif k == "linear":
                 call("clb_linear_fwd", _ptr(cur), _ptr(self.view(self.theta, op["w"])),
                      _ptr(self.view(self.theta, op["b"])) if op["b"] is not None else 0, _ptr(op["out"]),
@@ -514,7 +554,24 @@ class Engine:
             if cut_off and i == cut_op - 1:
                 from . import dist as _dist
                 self._dp_pending = _dist.start_tail_allreduce(self, cut_off)
-            if k == "linear":
+            if k == "linear" and op.get("planes"):
+                x_pl = op["inp"]                                      # planes of this layer's input
+                if not isinstance(d, (list, tuple)) and d.dim() == 1:  # fp32 gradient from the head: ReLU backward + planes
+                    nxt = self.dpl[pl_other]
+                    call("clb_planes_from_f32", _ptr(d), _ptr(op["out_pl"][0]), _ptr(nxt[0]), _ptr(nxt[1]), n * op["outf"], s)
+                    d, pl_other = nxt, pl_other ^ 1
+                self._timed(call, "clb_planes_linear_wgrad", _ptr(x_pl[0]), _ptr(x_pl[1]), _ptr(d[0]), _ptr(d[1]),
+                            _ptr(self.view(gdst, op["w"])), _ptr(self.view(gdst, op["b"])), _ptr(self.ws), self.ws.numel() * 4,
+                            n, op["inf"], op["outf"], imp_mode, _ptr(self.view(self.omega, op["w"])) if imp_mode else 0,
+                            imp_a, imp_b, s)
+                prev = self.ops[i - 1]
+                nxt = self.dpl[pl_other]
+                mask = _ptr(x_pl[0]) if (prev["kind"] == "linear" and prev.get("planes")) else 0     # ReLU of the Linear in front
+                self._timed(call, "clb_planes_linear_dgrad", _ptr(d[0]), _ptr(d[1]), _ptr(op["wt"][0]), _ptr(op["wt"][1]), mask,
+                            _ptr(nxt[0]), _ptr(nxt[1]), n, op["inf"], op["outf"], s)
+                d, pl_other = nxt, pl_other ^ 1
+                self.n_launch += 5
+            elif k == "linear":
                 if op["relu"]:
                     call("clb_relu_bwd", _ptr(d), _ptr(op["out"]), _ptr(d), n * op["outf"], s)
                 call("clb_linear_wgrad", _ptr(op["inp"]), _ptr(d), _ptr(self.view(gdst, op["w"])),
@@ -550,6 +607,11 @@ class Engine:
                     call("clb_planes_pool_bwd_nchw", _ptr(d[0]), _ptr(d[1]), _ptr(op["out_pl"][0]), _ptr(op["argmax"]),
                          _ptr(nxt), n, op["C"], op["H"], op["W"], s)
                     d, other = nxt, other ^ 1
+                elif op["lay_out"] == "planes_flat":                  # gradient / pooled activation as planes in flatten order
+                    nxt = self.dpl[pl_other]
+                    call("clb_planes_pool_bwd_flat", _ptr(d[0]), _ptr(d[1]), _ptr(op["out_pl"][0]), _ptr(op["argmax"]),
+                         _ptr(nxt[0]), _ptr(nxt[1]), n, op["H"], op["W"], op["C"], s)
+                    d, pl_other = nxt, pl_other ^ 1
                 else:
                     nxt = self.dpl[pl_other]
                     if op["lay_out"] == "nchw":                       # fp32 NCHW d (classifier side) -> planes

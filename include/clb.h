@@ -123,7 +123,8 @@ int clb_planes_conv_supported(int C, int H, int W, int K, int R, int S, int stri
 int clb_planes_weights(const float* w, void* wf_hi, void* wf_lo, void* wt_hi, void* wt_lo, int K, int C, void* stream);
 /* the same for n layers in ONE launch; every argument is a HOST array of n entries (device pointers / sizes), n <= 24 */
 int clb_planes_weights_batch(int n, const float* const* w, void* const* wf_hi, void* const* wf_lo, void* const* wt_hi, void* const* wt_lo,
-                              const int* K, const int* C, void* stream);
+                              const int* K, const int* C, const int* taps, void* stream);   /* taps[i]: 9 = conv [K][C][3][3], 1 = nn.Linear
+                                                                                               [K][C]; NULL = all 9 */
 /* y = conv3x3(x, w) + bias, optional fused ReLU; x planes [N][H][W][C], y planes [N][H][W][K]   (nn.Conv2d + nn.ReLU) */
 int clb_planes_conv_fwd(const void* x_hi, const void* x_lo, const void* wf_hi, const void* wf_lo, const float* bias, void* y_hi,
                         void* y_lo, int N, int H, int W, int C, int K, int relu, void* stream);
@@ -163,6 +164,28 @@ int clb_planes_pool_bwd(const void* dy_hi, const void* dy_lo, const float* dy_f3
 /* same with an fp32 NCHW result [N][C][H][W] (dY of a conv that does not run on the planes kernels) */
 int clb_planes_pool_bwd_nchw(const void* dy_hi, const void* dy_lo, const void* pooled_hi, const uint8_t* argmax, float* dx, int N, int C,
                              int H, int W, void* stream);
+
+/* nn.Linear (+ReLU) of the VGG classifiers (VGGSlim.py:58-73) on the same kernels: a 1x1 "conv" over a 1x1 map whose rows
+ * are the M samples.  in % 64 == out % 64 == 0.  x planes [M][in], y planes [M][out], weight planes from
+ * clb_planes_weights_batch with taps = 1 ([out][in] forward, [in][out] dgrad).  mask_hi / imp_* as for the convs. */
+int clb_planes_linear_supported(int in, int out);
+int clb_planes_linear_fwd(const void* x_hi, const void* x_lo, const void* wf_hi, const void* wf_lo, const float* bias, void* y_hi,
+                          void* y_lo, int M, int in, int out, int relu, void* stream);
+int clb_planes_linear_dgrad(const void* dy_hi, const void* dy_lo, const void* wt_hi, const void* wt_lo, const void* mask_hi, void* dx_hi,
+                            void* dx_lo, int M, int in, int out, void* stream);
+size_t clb_planes_linear_wgrad_ws(int M, int in, int out);
+int clb_planes_linear_wgrad(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, float* dw, float* dbias, float* ws,
+                            size_t ws_bytes, int M, int in, int out, int imp_mode, float* omega, float imp_a, float imp_b, void* stream);
+/* the conv / classifier boundary: max-pool whose output (backward: whose incoming gradient and pooled activation) are planes
+ * in the classifier's flatten order [N][C][H/2][W/2]  (x.view(x.size(0), -1), VGGSlim.py:66) */
+int clb_planes_pool_fwd_flat(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, uint8_t* argmax, int N, int H, int W, int C,
+                             void* stream);
+int clb_planes_pool_bwd_flat(const void* dy_hi, const void* dy_lo, const void* pooled_hi, const uint8_t* argmax, void* dx_hi, void* dx_lo,
+                             int N, int H, int W, int C, void* stream);
+/* element-wise layout changes at the edges of the planes pipeline: out = hi + lo;  (hi, lo) = split(x), zeroed where the
+ * activation whose hi plane is mask_hi (may be NULL) is <= 0 (ReLU backward) */
+int clb_planes_to_f32(const void* hi, const void* lo, float* out, int64_t n, void* stream);
+int clb_planes_from_f32(const float* x, const void* mask_hi, void* hi, void* lo, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Optimiser / importance streaming kernels (a4-a11).  One launch over the flat parameter buffer.

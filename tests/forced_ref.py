@@ -20,6 +20,10 @@ def _planes_to_nchw(pl, n, H, W, C):
     return (hi + lo).view(n, H, W, C).permute(0, 3, 1, 2)
 
 
+def _planes_flat(pl, numel):
+    return pl[0][:numel].view(torch.bfloat16).float() + pl[1][:numel].view(torch.bfloat16).float()
+
+
 def _audit(audit, name, wrong, margin_rel):
     k = int(wrong.sum().item())
     audit["decisions"] += wrong.numel()
@@ -53,6 +57,8 @@ def forced_reference(eng, x, y, loss_mode, denom=None, device="cpu"):
                 am = nxt["argmax"][:n * PH * PW * K].view(n, PH, PW, K).permute(0, 3, 1, 2).to(device).long()
                 if nxt.get("lay_out") == "planes":
                     pooled_gpu = _planes_to_nchw(nxt["out_pl"], n, PH, PW, K).to(device)
+                elif nxt.get("lay_out") == "planes_flat":            # planes in the classifier's flatten order [n][K][PH][PW]
+                    pooled_gpu = _planes_flat(nxt["out_pl"], n * K * PH * PW).view(n, K, PH, PW).to(device)
                 else:
                     pooled_gpu = nxt["out"][:n * K * PH * PW].view(n, K, PH, PW).to(device)
                 live = pooled_gpu > 0
@@ -89,7 +95,10 @@ def forced_reference(eng, x, y, loss_mode, denom=None, device="cpu"):
             if op["b"] is not None:
                 z = z + params[op["b"]]
             if op["relu"]:
-                mask = op["out"][:n * op["outf"]].view(n, op["outf"]).to(device) > 0
+                if op.get("planes"):
+                    mask = _planes_flat(op["out_pl"], n * op["outf"]).view(n, op["outf"]).to(device) > 0
+                else:
+                    mask = op["out"][:n * op["outf"]].view(n, op["outf"]).to(device) > 0
                 scale = z.detach().abs().max()
                 _audit(audit, "fc%d" % i, (z.detach() > 0) != mask, z.detach().abs() / scale)
                 a = z * mask.to(dt)

@@ -75,7 +75,7 @@ def test_weight_planes_layouts():
     wf2, wt2 = empty_planes(128, 9, 64), empty_planes(64, 9, 128)
     P, I = ctypes.c_void_p * 1, ctypes.c_int * 1
     c.call("clb_planes_weights_batch", 1, P(wd.data_ptr()), P(wf2[0].data_ptr()), P(wf2[1].data_ptr()), P(wt2[0].data_ptr()),
-           P(wt2[1].data_ptr()), I(128), I(64), S())
+           P(wt2[1].data_ptr()), I(128), I(64), I(9), S())
     assert all(torch.equal(a, b) for a, b in zip(wf + wt, wf2 + wt2))
 
 
@@ -224,7 +224,7 @@ def _full_net(name, B, ref_device):
             if hasattr(m, "weight"):
                 m.weight.mul_(10.0)
     eng = Engine(model, (3, 64, 64), B)
-    assert sum(1 for op in eng.ops if op.get("planes")) >= 5 and eng.ops[0].get("fused_first"), "planes pipeline not active"
+    assert sum(1 for op in eng.ops if op.get("planes")) >= 7 and eng.ops[0].get("fused_first"), "planes pipeline not active"
     g = torch.Generator().manual_seed(5)
     x = torch.randn(B, 3, 64, 64, generator=g).to(DEV)
     y = torch.randint(0, 20, (B,), generator=g).to(DEV)
@@ -294,3 +294,71 @@ def test_full_batch_properties_default_mode():
     eng.fwd_loss_bwd(x[100:], y[100:], LOSS_SUM_NLL, train=False)
     for i, (n, _) in enumerate(model.named_parameters()):
         assert rel_err(eng.view(half + eng.grad, i), eng.view(full, i)) <= 5e-5, n
+
+
+@pytest.mark.parametrize("M,fin,fout", [(200, 2048, 512), (25, 512, 512), (7, 64, 128), (200, 9216, 4096)])
+def test_linear_on_planes_kernels(M, fin, fout):
+    """nn.Linear (+ReLU) as a 1x1 'conv' over a 1x1 map on the planes kernels (VGG classifier shapes, AlexNet's 9216 -> 4096,
+    ragged row counts): fwd / dgrad (+ fused ReLU mask) / wgrad / bias grad against fp64."""
+    import ctypes
+    c = capi()
+    g = torch.Generator().manual_seed(fin + M)
+    x = quant(torch.relu(torch.randn(M, fin, generator=g)))
+    w = torch.randn(fout, fin, generator=g) * (2.0 / fin) ** 0.5
+    b = torch.randn(fout, generator=g) * 0.1
+    xp = to_planes(x)
+    wd, bd = w.to(DEV), b.to(DEV)
+    wf, wt = empty_planes(fout, fin), empty_planes(fin, fout)
+    P, I = ctypes.c_void_p * 1, ctypes.c_int * 1
+    c.call("clb_planes_weights_batch", 1, P(wd.data_ptr()), P(wf[0].data_ptr()), P(wf[1].data_ptr()), P(wt[0].data_ptr()),
+           P(wt[1].data_ptr()), I(fout), I(fin), I(1), S())
+    wq = quant(w)
+    assert torch.equal(from_planes(wf), wq) and torch.equal(from_planes(wt), wq.t().contiguous())
+    y = empty_planes(M, fout)
+    c.call("clb_planes_linear_fwd", xp[0].data_ptr(), xp[1].data_ptr(), wf[0].data_ptr(), wf[1].data_ptr(), bd.data_ptr(), y[0].data_ptr(),
+           y[1].data_ptr(), M, fin, fout, 1, S())
+    ref = torch.relu(x.double() @ wq.double().t() + b.double())
+    assert rel_err(from_planes(y), ref) <= KERNEL_TOL, "fwd"
+    yf = torch.zeros(M, fout, device=DEV)
+    c.call("clb_planes_to_f32", y[0].data_ptr(), y[1].data_ptr(), yf.data_ptr(), M * fout, S())
+    assert torch.equal(yf.cpu(), from_planes(y))
+    dy32 = torch.randn(M, fout, generator=g)
+    dyp = empty_planes(M, fout)
+    c.call("clb_planes_from_f32", dy32.to(DEV).data_ptr(), y[0].data_ptr(), dyp[0].data_ptr(), dyp[1].data_ptr(), M * fout, S())
+    dy = quant(dy32 * (ref > 0))                                    # ReLU backward fused into the conversion
+    assert torch.equal(from_planes(dyp), dy)
+    dx = empty_planes(M, fin)
+    c.call("clb_planes_linear_dgrad", dyp[0].data_ptr(), dyp[1].data_ptr(), wt[0].data_ptr(), wt[1].data_ptr(), xp[0].data_ptr(),
+           dx[0].data_ptr(), dx[1].data_ptr(), M, fin, fout, S())
+    assert rel_err(from_planes(dx), (dy.double() @ wq.double()) * (x > 0)) <= KERNEL_TOL, "dgrad + mask"
+    ws_bytes = c.lib().clb_planes_linear_wgrad_ws(M, fin, fout)
+    ws = torch.zeros(ws_bytes // 4 + 4, device=DEV)
+    dw, db = torch.zeros(fout, fin, device=DEV), torch.zeros(fout, device=DEV)
+    om = torch.full((fout, fin), 0.25, device=DEV)
+    c.call("clb_planes_linear_wgrad", xp[0].data_ptr(), xp[1].data_ptr(), dyp[0].data_ptr(), dyp[1].data_ptr(), dw.data_ptr(), db.data_ptr(),
+           ws.data_ptr(), ws_bytes, M, fin, fout, 1, om.data_ptr(), 100.0, 0.0, S())
+    assert rel_err(dw, dy.double().t() @ x.double()) <= KERNEL_TOL, "wgrad"
+    assert rel_err(db, dy.double().sum(0)) <= KERNEL_TOL, "bias grad"
+    assert rel_err(om, 0.25 + dw.double().cpu() ** 2 / 100.0) <= 1e-6
+
+
+def test_pool_flat_planes_boundary():
+    """The conv / classifier boundary: pooled planes in the flatten order [N][C][PH][PW] and their backward."""
+    c = capi()
+    g = torch.Generator().manual_seed(9)
+    N, C, H, W = 5, 128, 4, 4
+    x = quant(torch.relu(torch.randn(N, C, H, W, generator=g)))
+    xp = to_planes(x.permute(0, 2, 3, 1).contiguous())
+    y = empty_planes(N, C * (H // 2) * (W // 2))
+    am = torch.zeros(N, H // 2, W // 2, C, dtype=torch.uint8, device=DEV)
+    c.call("clb_planes_pool_fwd_flat", xp[0].data_ptr(), xp[1].data_ptr(), y[0].data_ptr(), y[1].data_ptr(), am.data_ptr(), N, H, W, C, S())
+    ref = F.max_pool2d(x, 2, 2)
+    assert torch.equal(from_planes(y).view(N, C, H // 2, W // 2), ref)
+    dy = quant(torch.randn(N, C, H // 2, W // 2, generator=g))
+    dyp = to_planes(dy.reshape(N, -1))
+    xr = x.clone().requires_grad_(True)
+    F.max_pool2d(xr, 2, 2).backward(dy)
+    dx = empty_planes(N, H, W, C)
+    c.call("clb_planes_pool_bwd_flat", dyp[0].data_ptr(), dyp[1].data_ptr(), y[0].data_ptr(), am.data_ptr(), dx[0].data_ptr(), dx[1].data_ptr(),
+           N, H, W, C, S())
+    assert torch.equal(from_planes(dx).permute(0, 3, 1, 2), xr.grad * (x > 0))

@@ -14,8 +14,16 @@ from clsurvey_b200 import _capi
 from clsurvey_b200.engine import get_engine
 from clsurvey_b200.models import make_alexnet, make_vgg
 
+from clsurvey_b200 import dist as cdist
 _capi.lib()
-dev = torch.device("cuda")
+cdist.init()                                  # under torchrun: data-parallel (rows of every mini-batch / whole importance batches)
+dev = torch.device("cuda", torch.cuda.current_device())
+_print = print
+
+
+def print(*a, **k):                           # one line per config, from rank 0
+    if cdist.rank() == 0:
+        _print(*a, **k)
 
 
 class DS(torch.utils.data.TensorDataset):
@@ -32,7 +40,8 @@ def dsets(t):
 
 
 def loaders(d, bs=200):
-    return {k: torch.utils.data.DataLoader(v, batch_size=bs, shuffle=False) for k, v in d.items()}
+    from clsurvey_b200.data import CachedLoader                 # the device-resident task cache the entry points use (8f-2)
+    return {k: CachedLoader(v, bs, shuffle=False, device=dev) for k, v in d.items()}
 
 
 def timed(fn):
@@ -66,7 +75,8 @@ def penalty_config(tag, which, model):
     from clsurvey_b200.methods import trainers
     tr_s = trainers.LAST_RUN["train_seconds"]
     print(json.dumps({"config": tag, "importance_pass_images_per_s": 8000 / t_imp, "importance_pass_s": t_imp,
-                      "train_images_per_s": trainers.LAST_RUN["train_images"] / tr_s, "two_epochs_incl_val_and_checkpoints_s": t_ep}), flush=True)
+                      "train_images_per_s": trainers.LAST_RUN["train_images"] / tr_s, "two_epochs_incl_val_and_checkpoints_s": t_ep,
+                      "n_gpus": cdist.world_size()}), flush=True)
 
 
 def si_config():
@@ -84,7 +94,8 @@ def si_config():
     tr_s = trainers.LAST_RUN["train_seconds"]
     _, t_c = timed(lambda: T.update_reg_params(model))
     print(json.dumps({"config": "C4 SI VGG-11", "train_images_per_s": trainers.LAST_RUN["train_images"] / tr_s,
-                      "epochs_run": len([e for e in trainers.LAST_RUN["epochs"] if e[1] == "train"]), "consolidation_s": t_c}), flush=True)
+                      "epochs_run": len([e for e in trainers.LAST_RUN["epochs"] if e[1] == "train"]), "consolidation_s": t_c,
+                      "n_gpus": cdist.world_size()}), flush=True)
 
 
 def gem_config():
@@ -118,3 +129,4 @@ if __name__ == "__main__":
     if "C3" in which: penalty_config("C3 MAS VGG-11", "mas", make_vgg("VGG11_cl_512_512"))
     if "C4" in which: si_config()
     if "C5" in which: gem_config()
+    cdist.shutdown()

@@ -306,7 +306,7 @@ def run_gpu_arm(args):
     ms = timed(step_dev, args.steps)
     value = GLOBAL_BATCH * args.steps / (ms / 1e3)
     mode_name = {0: "fp32 FFMA (SIMT)", 1: "tf32x3 tcgen05", 2: "tf32x1 tcgen05",
-                 3: "bf16x3 tcgen05: TMA-fed NHWC hi/lo planes (conv) + tf32x3 (linear)"}[args.mm_mode]
+                 3: "bf16x3 tcgen05: TMA-fed NHWC hi/lo planes (conv + hidden Linear layers) + tf32x3 (task head)"}[args.mm_mode]
     # per-kernel timing of the dominant (conv) launches: the same K steps run eagerly with CUDA events around every conv
     # call (events cannot be read back from inside a replayed graph)
     l0 = _capi.lib().clb_launch_count()

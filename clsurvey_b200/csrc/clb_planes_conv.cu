@@ -164,7 +164,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                         tma::load_4d(st, &map_a_hi, full + 8 * s, cb * 64, sx - p.pad, h0 + r - p.pad, n0);
                         tma::load_4d(st + kTileBytes, &map_a_lo, full + 8 * s, cb * 64, sx - p.pad, h0 + r - p.pad, n0);
                         tma::load_2d(st + 2 * kTileBytes, &map_b_hi, full + 8 * s, kb * 64, nt * BN);
-                        tma::load_2d(st + 3 * kTileBytes, &map_b_lo, full + 8 * s, kb * 64, nt * BN);
+                        tma::load_2d(st + 2 * kTileBytes + kBBytes, &map_b_lo, full + 8 * s, kb * 64, nt * BN);
                     }
                 } else {
                     const int mt = item % p.n_tiles_m, nt = (item / p.n_tiles_m) % p.n_tiles_n;
@@ -198,10 +198,11 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             uint32_t it = 0, ccount = 0;                  // ccount: accumulator chunks issued so far (chunk c uses set c & 1)
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 int nkb;
-                uint32_t idesc;
+                uint32_t idesc, idesc_wide = 0;
                 if (KIND == 0) {
                     nkb = p.taps * cpb;
                     idesc = idesc_bf16(BN, false);
+                    idesc_wide = idesc_bf16(2 * BN, false);
                 } else {
                     const int nt = (item / p.n_tiles_m) % p.n_tiles_n, z = item / (p.n_tiles_m * p.n_tiles_n);
                     const int kb0 = z * p.kb_per_split;
@@ -223,13 +224,15 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                     tc_fence_after();
                     const uint32_t st = base + (uint32_t)s * kStageBytes;
                     if (KIND == 0) {
+                        // B_lo lies right behind B_hi, and the cross accumulator right behind the main one: ONE N = 2 BN
+                        // instruction computes A_hi.[B_hi | B_lo] -> [main | cross] and reads A_hi from shared memory once
+                        // (20 KB instead of 24 KB of operand reads per K step -- the kernel is shared-memory bound)
                         const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + kTileBytes);
-                        const uint64_t b_hi = make_desc(st + 2 * kTileBytes), b_lo = make_desc(st + 3 * kTileBytes);
+                        const uint64_t b_hi = make_desc(st + 2 * kTileBytes);
 #pragma unroll
                         for (int k = 0; k < BKP / 16; ++k) {
-                            umma_bf16_ss(d_cross, a_lo + 2 * k, b_hi + 2 * k, idesc, (ic | k) != 0);
-                            umma_bf16_ss(d_cross, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
-                            umma_bf16_ss(d_main, a_hi + 2 * k, b_hi + 2 * k, idesc, (ic | k) != 0);
+                            umma_bf16_ss(d_main, a_hi + 2 * k, b_hi + 2 * k, idesc_wide, (ic | k) != 0);
+                            umma_bf16_ss(d_cross, a_lo + 2 * k, b_hi + 2 * k, idesc, 1);
                         }
                     } else {
 #pragma unroll
@@ -238,6 +241,7 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
                             const uint64_t a_hi = make_desc_mn(st + o, p.mn_lbo, p.mn_sbo), a_lo = make_desc_mn(st + kTileBytes + o, p.mn_lbo, p.mn_sbo);
                             const uint64_t b_hi = make_desc_mn(st + 2 * kTileBytes + o, p.mn_lbo, p.mn_sbo);
                             const uint64_t b_lo = make_desc_mn(st + 3 * kTileBytes + o, p.mn_lbo, p.mn_sbo);
+                            // (the N = 256 form over [X_hi | X_lo] measured 7 % SLOWER with MN-major operands: three MMAs here)
                             umma_bf16_ss(d_cross, a_lo, b_hi, idesc, (ic | k) != 0);
                             umma_bf16_ss(d_cross, a_hi, b_lo, idesc, 1);
                             umma_bf16_ss(d_main, a_hi, b_hi, idesc, (ic | k) != 0);

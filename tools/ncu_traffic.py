@@ -1,4 +1,6 @@
-"""profiles/r2_conv_traffic.json from an `ncu --set full` raw CSV of ONE bench step's conv-stack launches:
+"""profiles/r2_conv_traffic.json from an `ncu --set full` raw CSV of the bench's conv-stack launches (the capture may hold
+more than one step: the first period of the kernel-name sequence is used):
+    CLB_PLANES_LINEAR=0 ncu --set full --clock-control none -k regex:"conv_planes|conv1_|wgrad_reduce|bias_" -c 140 ... bench.py
     ncu -i gpurun_out/x/conv_full.ncu-rep --page raw --csv > /tmp/raw.csv ; python tools/ncu_traffic.py /tmp/raw.csv
 Also prints the per-launch table (time, tensor-pipe %, DRAM bytes) that profiles/README.md quotes."""
 import csv, json, os, re, sys
@@ -14,7 +16,14 @@ def to_bytes(v, u):
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
 ur, uw = units[col["dram__bytes_read.sum"]], units[col["dram__bytes_write.sum"]]
 tot, out = 0.0, []
-for r in rows[2:]:
+body = rows[2:]
+names = [re.sub(r"\(.*", "", r[col["Kernel Name"]]) for r in body]
+period = len(body)
+for q in range(8, len(body) // 2 + 1):                    # one step = the shortest period of the launch sequence
+    if names[:q] == names[q:2 * q]:
+        period = q
+        break
+for r in body[:period]:
     name = re.sub(r"\(.*", "", r[col["Kernel Name"]]).replace("void ", "")
     rd, wr = to_bytes(get(r, "dram__bytes_read.sum"), ur), to_bytes(get(r, "dram__bytes_write.sum"), uw)
     t = get(r, "gpu__time_duration.sum")

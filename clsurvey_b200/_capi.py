@@ -41,6 +41,8 @@ SIGNATURES = {
     "clb_planes_conv_supported": [c_i] * 8,
     "clb_planes_weights": [c_p] * 5 + [c_i, c_i, c_p],
     "clb_planes_weights_batch": [c_i] + [c_p] * 9,
+    "clb_planes_defer_join": [c_i],
+    "clb_planes_join": [c_p],
     "clb_planes_linear_supported": [c_i, c_i],
     "clb_planes_linear_fwd": [c_p] * 7 + [c_i] * 4 + [c_p],
     "clb_planes_linear_dgrad": [c_p] * 7 + [c_i] * 3 + [c_p],

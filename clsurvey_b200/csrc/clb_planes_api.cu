@@ -26,6 +26,62 @@ int wgrad_reduce(const float* ws, float* dw, float* omega, int K, int C, int tap
 using namespace clb;
 typedef uint16_t u16;
 
+// Side stream.  The memory-bound helpers of a layer -- the bias gradient (column sums of dY), the split-K reduction of dW and the
+// weight -> planes conversion -- need a few KB of shared memory and <= 40 registers per thread, so their CTAs fit on the SMs next
+// to the one persistent CTA of a tcgen05 GEMM (shared-memory / tensor bound).  They are forked off the caller's stream onto one
+// side stream per device and joined back
+//   - before the call returns (default): callers, and a CUDA graph being captured on their stream, see one ordered call;
+//   - or, after clb_planes_defer_join(1), at the caller's next clb_planes_join(stream): the engine issues the dgrad GEMM of the
+//     same layer (resp. the fp32 first-layer kernel) in between, which touches neither the workspace nor dW.
+// CLB_BIAS_SIDE=0 keeps everything on the caller's stream.
+namespace {
+struct Side { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, fork2 = nullptr, join = nullptr; int pending = 0; };
+int g_defer_join = 0;
+Side* side_of_current_device() {
+    static Side sides[32];
+    static int enabled = -1;
+    if (enabled < 0) { const char* e = getenv("CLB_BIAS_SIDE"); enabled = (e && e[0] == '0') ? 0 : 1; }
+    int dev = 0;
+    if (!enabled || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return nullptr;
+    Side& sd = sides[dev];
+    if (!sd.st) {
+        if (cudaStreamCreateWithFlags(&sd.st, cudaStreamNonBlocking) != cudaSuccess) { sd.st = nullptr; return nullptr; }
+        cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&sd.fork2, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming);
+    }
+    return &sd;
+}
+void side_join_pending(Side* sd, cudaStream_t s) {      // a deferred join nobody collected yet: collect it now
+    if (sd && sd->pending) { cudaStreamWaitEvent(s, sd->join, 0); sd->pending = 0; }
+}
+Side* side_fork(cudaStream_t s) {                       // the side stream now waits for everything queued on s so far
+    Side* sd = side_of_current_device();
+    side_join_pending(sd, s);
+    if (sd && cudaEventRecord(sd->fork, s) == cudaSuccess && cudaStreamWaitEvent(sd->st, sd->fork, 0) == cudaSuccess) return sd;
+    return nullptr;
+}
+void side_fork_again(Side* sd, cudaStream_t s) {        // ... and for what was queued on s since
+    if (sd && cudaEventRecord(sd->fork2, s) == cudaSuccess) cudaStreamWaitEvent(sd->st, sd->fork2, 0);
+}
+void side_join(Side* sd, cudaStream_t s, bool may_defer) {
+    if (!sd || cudaEventRecord(sd->join, sd->st) != cudaSuccess) return;
+    if (may_defer && g_defer_join) sd->pending = 1;
+    else cudaStreamWaitEvent(s, sd->join, 0);
+}
+// dW = sum of the split-K partials (+ importance), db = column sums of dY: on the side stream when there is one
+int wgrad_tail(Side* sd, cudaStream_t s, const float* ws, float* dw, float* omega, int K, int C, int taps, int splits, int imp_mode,
+               float imp_a, float imp_b, const u16* dy_hi, const u16* dy_lo, float* dbias, float* part, int64_t rows) {
+    cudaStream_t t = sd ? sd->st : s;
+    int rc = CLB_OK;
+    if (dbias) rc = pl::bias_grad(dy_hi, dy_lo, dbias, part, rows, K, t);       // independent of the GEMM: runs next to it
+    side_fork_again(sd, s);                                                      // the reduction needs the partials
+    if (!rc) rc = pl::wgrad_reduce(ws, dw, omega, K, C, taps, splits, imp_mode, imp_a, imp_b, t);
+    side_join(sd, s, true);
+    return rc;
+}
+}  // namespace
+
 extern "C" {
 
 int clb_planes_conv_supported(int C, int H, int W, int K, int R, int S, int stride, int pad) {
@@ -47,9 +103,22 @@ int clb_planes_weights_batch(int n, const float* const* w, void* const* wf_hi, v
         CLB_CHECK_ARG(w[i] && wf_hi[i] && wf_lo[i] && wt_hi[i] && wt_lo[i] && K[i] > 0 && C[i] > 0 && (K[i] % 2) == 0 && (C[i] % 2) == 0);
         CLB_CHECK_ARG(taps == nullptr || taps[i] == 1 || taps[i] == 9);
     }
-    int rc = pl::weights_to_planes_batch(n, w, wf_hi, wf_lo, wt_hi, wt_lo, K, C, taps, as_stream(stream));
+    cudaStream_t s = as_stream(stream);
+    Side* sd = g_defer_join ? side_fork(s) : nullptr;   // worth a fork only when the caller has work to put next to it
+    int rc = pl::weights_to_planes_batch(n, w, wf_hi, wf_lo, wt_hi, wt_lo, K, C, taps, sd ? sd->st : s);
+    side_join(sd, s, true);
     if (rc) return rc;
     CLB_CHECK_LAUNCH();
+    return CLB_OK;
+}
+
+int clb_planes_defer_join(int on) {
+    g_defer_join = on ? 1 : 0;
+    return CLB_OK;
+}
+
+int clb_planes_join(void* stream) {
+    side_join_pending(side_of_current_device(), as_stream(stream));
     return CLB_OK;
 }
 
@@ -92,18 +161,14 @@ int clb_planes_conv_wgrad(const void* x_hi, const void* x_lo, const void* dy_hi,
     }
     cudaStream_t s = as_stream(stream);
     int splits = 0;
+    Side* sd = side_fork(s);
     int rc = pl::conv_wgrad_partials((const u16*)x_hi, (const u16*)x_lo, (const u16*)dy_hi, (const u16*)dy_lo, ws, &splits, N, H, W, C, K, 9, s);
+    float* part = ws + ((pl::wgrad_ws_floats(N, H, W, C, K, 9) + 3) & ~(size_t)3);
+    if (rc) side_join(sd, s, false);
+    else rc = wgrad_tail(sd, s, ws, dw, omega, K, C, 9, splits, imp_mode, imp_a, imp_b, (const u16*)dy_hi, (const u16*)dy_lo, dbias, part,
+                         (int64_t)N * H * W);
     if (rc) return rc;
     CLB_CHECK_LAUNCH();
-    rc = pl::wgrad_reduce(ws, dw, omega, K, C, 9, splits, imp_mode, imp_a, imp_b, s);
-    if (rc) return rc;
-    CLB_CHECK_LAUNCH();
-    if (dbias) {
-        float* part = ws + ((pl::wgrad_ws_floats(N, H, W, C, K, 9) + 3) & ~(size_t)3);
-        rc = pl::bias_grad((const u16*)dy_hi, (const u16*)dy_lo, dbias, part, (int64_t)N * H * W, K, s);
-        if (rc) return rc;
-        CLB_CHECK_LAUNCH();
-    }
     return CLB_OK;
 }
 
@@ -178,18 +243,14 @@ int clb_planes_linear_wgrad(const void* x_hi, const void* x_lo, const void* dy_h
     if (ws_bytes < clb_planes_linear_wgrad_ws(M, in, out)) { set_error("clb_planes_linear_wgrad: workspace too small"); return CLB_EWORKSPACE; }
     cudaStream_t s = as_stream(stream);
     int splits = 0;
+    Side* sd = side_fork(s);
     int rc = pl::conv_wgrad_partials((const u16*)x_hi, (const u16*)x_lo, (const u16*)dy_hi, (const u16*)dy_lo, ws, &splits, M, 1, 1, in, out, 1, s);
+    float* part = ws + ((pl::wgrad_ws_floats(M, 1, 1, in, out, 1) + 3) & ~(size_t)3);
+    if (rc) side_join(sd, s, false);
+    else rc = wgrad_tail(sd, s, ws, dw, omega, out, in, 1, splits, imp_mode, imp_a, imp_b, (const u16*)dy_hi, (const u16*)dy_lo, dbias, part,
+                         (int64_t)M);
     if (rc) return rc;
     CLB_CHECK_LAUNCH();
-    rc = pl::wgrad_reduce(ws, dw, omega, out, in, 1, splits, imp_mode, imp_a, imp_b, s);
-    if (rc) return rc;
-    CLB_CHECK_LAUNCH();
-    if (dbias) {
-        float* part = ws + ((pl::wgrad_ws_floats(M, 1, 1, in, out, 1) + 3) & ~(size_t)3);
-        rc = pl::bias_grad((const u16*)dy_hi, (const u16*)dy_lo, dbias, part, (int64_t)M, out, s);
-        if (rc) return rc;
-        CLB_CHECK_LAUNCH();
-    }
     return CLB_OK;
 }
 

@@ -335,7 +335,7 @@ int pool_bwd_to_nchw(const uint16_t* dy_hi, const uint16_t* dy_lo, const uint16_
 // db[k] = sum over pixels of dY[pix][k].  Two deterministic stages: kBiasChunks CTAs sum a contiguous pixel range each (thread =
 // channel pair, fixed order), then one pass adds the chunk partials in order.  No atomics: bit-reproducible.
 constexpr int kBiasChunks = 592;
-__global__ void __launch_bounds__(256) bias_partials_kernel(const uint16_t* __restrict__ dy_hi, const uint16_t* __restrict__ dy_lo,
+__global__ void __launch_bounds__(256, 6) bias_partials_kernel(const uint16_t* __restrict__ dy_hi, const uint16_t* __restrict__ dy_lo,
                                                             float* __restrict__ part, int64_t npix, int K, int64_t pix_per_chunk) {
     // thread = 8 channels (one 16-byte load per plane) of every `rows`-th pixel of the chunk; channel groups beyond the CTA's
     // 256 threads are handled in further passes

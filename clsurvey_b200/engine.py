@@ -395,8 +395,10 @@ class Engine:
         self._n = n
         self._train = train
         self._masks = {}
+        wjoin = False
         if self._wbatch is not None:      # weights of all planes convs -> bf16 hi/lo planes (fwd + dgrad layouts), one launch
-            call("clb_planes_weights_batch", *self._wbatch, s)
+            wjoin = bool(self.ops and self.ops[0].get("fused_first"))
+            self._side_call(wjoin, "clb_planes_weights_batch", *self._wbatch, s)
             self.n_launch += 1
         for op in self.ops:
             op["inp"] = cur
@@ -407,6 +409,9 @@ class Engine:
                 self._timed(call, "clb_planes_conv1_pool_fwd", _ptr(cur), _ptr(self.view(self.theta, op["w"])),
                             _ptr(self.view(self.theta, op["b"])), _ptr(out[0]), _ptr(out[1]), _ptr(pool["argmax"]), n, op["C"],
                             op["H"], op["W"], op["K"], s)
+                if wjoin:                 # the fp32 first layer ran next to the weight conversion on the side stream
+                    call("clb_planes_join", s)
+                    wjoin = False
                 cur = out
             elif k == "maxpool" and op.get("fused_prev"):
                 continue                                              # done by the conv kernel in front
@@ -560,7 +565,7 @@ class Engine:
                     nxt = self.dpl[pl_other]
                     call("clb_planes_from_f32", _ptr(d), _ptr(op["out_pl"][0]), _ptr(nxt[0]), _ptr(nxt[1]), n * op["outf"], s)
                     d, pl_other = nxt, pl_other ^ 1
-                self._timed(call, "clb_planes_linear_wgrad", _ptr(x_pl[0]), _ptr(x_pl[1]), _ptr(d[0]), _ptr(d[1]),
+                self._timed(self._side_call, True, "clb_planes_linear_wgrad", _ptr(x_pl[0]), _ptr(x_pl[1]), _ptr(d[0]), _ptr(d[1]),
                             _ptr(self.view(gdst, op["w"])), _ptr(self.view(gdst, op["b"])), _ptr(self.ws), self.ws.numel() * 4,
                             n, op["inf"], op["outf"], imp_mode, _ptr(self.view(self.omega, op["w"])) if imp_mode else 0,
                             imp_a, imp_b, s)
@@ -569,6 +574,7 @@ class Engine:
                 mask = _ptr(x_pl[0]) if (prev["kind"] == "linear" and prev.get("planes")) else 0     # ReLU of the Linear in front
                 self._timed(call, "clb_planes_linear_dgrad", _ptr(d[0]), _ptr(d[1]), _ptr(op["wt"][0]), _ptr(op["wt"][1]), mask,
                             _ptr(nxt[0]), _ptr(nxt[1]), n, op["inf"], op["outf"], s)
+                call("clb_planes_join", s)                           # split-K reduce + bias grad of this layer (side stream)
                 d, pl_other = nxt, pl_other ^ 1
                 self.n_launch += 5
             elif k == "linear":
@@ -625,7 +631,7 @@ class Engine:
                 self.n_launch += 1
             elif k == "conv" and op.get("planes"):
                 x_pl = op["inp"]                                      # planes of this conv's (post-ReLU) input
-                self._timed(call, "clb_planes_conv_wgrad", _ptr(x_pl[0]), _ptr(x_pl[1]), _ptr(d[0]), _ptr(d[1]),
+                self._timed(self._side_call, True, "clb_planes_conv_wgrad", _ptr(x_pl[0]), _ptr(x_pl[1]), _ptr(d[0]), _ptr(d[1]),
                             _ptr(self.view(gdst, op["w"])), _ptr(self.view(gdst, op["b"])), _ptr(self.ws), self.ws.numel() * 4,
                             n, op["H"], op["W"], op["C"], op["K"], imp_mode,
                             _ptr(self.view(self.omega, op["w"])) if imp_mode else 0, imp_a, imp_b, s)
@@ -637,6 +643,7 @@ class Engine:
                     relu_done.add(i - 1)
                 self._timed(call, "clb_planes_conv_dgrad", _ptr(d[0]), _ptr(d[1]), _ptr(op["wt"][0]), _ptr(op["wt"][1]), mask,
                             _ptr(nxt[0]), _ptr(nxt[1]), n, op["H"], op["W"], op["C"], op["K"], s)
+                call("clb_planes_join", s)                           # split-K reduce + bias grad of this layer (side stream)
                 d, pl_other = nxt, pl_other ^ 1
                 self.n_launch += 5
             elif k == "maxpool":
@@ -671,6 +678,18 @@ class Engine:
                 else:
                     call("clb_mas_accum", _ptr(self.omega[off:]), _ptr(self.grad[off:]), imp_a, imp_b, cnt, s)
                 self.n_launch += 1
+
+    def _side_call(self, defer, name, *args):
+        """A planes call whose memory-bound tail runs on the library's side stream; defer=True leaves the join to the
+        caller's clb_planes_join (include/clb.h), which must follow before anything reads the call's results.  Not while
+        bench.py times the calls one by one: each call then carries its own tail."""
+        if not defer or self.conv_events is not None:
+            return call(name, *args)
+        call("clb_planes_defer_join", 1)
+        try:
+            return call(name, *args)
+        finally:
+            call("clb_planes_defer_join", 0)
 
     def zero_grad(self):
         call("clb_memset_zero", _ptr(self.grad), self.grad.numel() * 4, _stream())

@@ -22,6 +22,13 @@ from ..engine import LOSS_MEAN_CE, engine_of
 
 LAST_RUN = {}     # diagnostics of the most recent train_model call (per-batch losses etc.); not part of the API
 
+_builtin_print = print
+
+
+def print(*a, **k):           # the reference's progress lines, once per job: data-parallel ranks > 0 stay silent
+    if cdist.rank() == 0:
+        _builtin_print(*a, **k)
+
 
 class _CheckpointWriter:
     """best_model.pth.tar / epoch.pth.tar (train_EWC.py:207-227) written by a background thread.

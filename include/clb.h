@@ -125,6 +125,13 @@ int clb_planes_weights(const float* w, void* wf_hi, void* wf_lo, void* wt_hi, vo
 int clb_planes_weights_batch(int n, const float* const* w, void* const* wf_hi, void* const* wf_lo, void* const* wt_hi, void* const* wt_lo,
                               const int* K, const int* C, const int* taps, void* stream);   /* taps[i]: 9 = conv [K][C][3][3], 1 = nn.Linear
                                                                                                [K][C]; NULL = all 9 */
+/* The memory-bound helpers of the planes calls (weight conversion above; split-K reduction and bias gradient of the wgrad calls
+ * below) run on a per-device side stream next to the tcgen05 GEMMs.  By default every call joins that stream before it returns.
+ * After clb_planes_defer_join(1) those calls return with the join pending and the caller collects it with clb_planes_join(stream)
+ * -- after queueing work that depends neither on their results nor on the workspace (the engine: the dgrad GEMM of the same layer,
+ * train_EWC.py:171 loss.backward()).  A pending join is also collected by the next call that forks.  Process-wide switch. */
+int clb_planes_defer_join(int on);
+int clb_planes_join(void* stream);
 /* y = conv3x3(x, w) + bias, optional fused ReLU; x planes [N][H][W][C], y planes [N][H][W][K]   (nn.Conv2d + nn.ReLU) */
 int clb_planes_conv_fwd(const void* x_hi, const void* x_lo, const void* wf_hi, const void* wf_lo, const float* bias, void* y_hi,
                         void* y_lo, int N, int H, int W, int C, int K, int relu, void* stream);

@@ -12,3 +12,4 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv
     python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline > /dev/null 2>&1; echo "ncu full rc=$?"
 # read here with: ncu -i gpurun_out/prof_conv.ncu-rep --page raw --csv > profiles/rN_ncu_full_conv.csv
 #                 python tools/ncu_traffic.py profiles/rN_ncu_full_conv.csv > profiles/rN_conv_traffic.json
+timeout 300 python tools/stream_bench.py > gpurun_out/stream_kernels.jsonl 2> gpurun_out/stream.err; echo "stream bench rc=$?"

@@ -23,6 +23,7 @@ SIGNATURES = {
     "clb_get_matmul_mode": [],
     "clb_launch_count": [],
     "clb_memset_zero": [c_p, c_sz, c_p],
+    "clb_stream_create": [c_p],
     "clb_conv2d_fwd": [c_p, c_p, c_p, c_p, c_p] + [c_i] * 10 + [c_p],
     "clb_conv2d_dgrad": [c_p, c_p, c_p, c_p] + [c_i] * 9 + [c_p],
     "clb_conv2d_wgrad_ws": [c_i] * 9,
@@ -112,3 +113,21 @@ def call(name, *args):
     rc = getattr(lib(), name)(*args)
     if rc != 0:
         raise ClbError("%s failed (rc=%d): %s" % (name, rc, lib().clb_last_error().decode()))
+
+
+_PRIVATE_STREAMS = {}
+
+
+def private_stream(name):
+    """A process-wide torch stream (one per name and device) backed by clb_stream_create: never shared with torch's pooled
+    streams, hence never the stream a CUDA graph is being captured on."""
+    import ctypes
+    import torch
+    key = (name, torch.cuda.current_device())
+    st = _PRIVATE_STREAMS.get(key)
+    if st is None:
+        h = ctypes.c_void_p()
+        call("clb_stream_create", ctypes.byref(h))
+        st = torch.cuda.ExternalStream(h.value)
+        _PRIVATE_STREAMS[key] = st
+    return st

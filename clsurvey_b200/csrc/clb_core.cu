@@ -59,6 +59,13 @@ int clb_set_matmul_mode(int mode) {
 }
 int clb_get_matmul_mode(void) { return clb::mm_mode(); }
 unsigned long long clb_launch_count(void) { return clb::launches(); }
+int clb_stream_create(void** out) {
+    CLB_CHECK_ARG(out != nullptr);
+    cudaStream_t st = nullptr;
+    CLB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    *out = (void*)st;
+    return CLB_OK;
+}
 int clb_memset_zero(void* p, size_t bytes, void* stream) {
     CLB_CHECK_ARG(p != nullptr || bytes == 0);
     if (bytes) CLB_CUDA(cudaMemsetAsync(p, 0, bytes, clb::as_stream(stream)));

@@ -107,7 +107,7 @@ def allreduce_flat(t):
 
 def _comm_stream():
     if _state.get("stream") is None:
-        _state["stream"] = torch.cuda.Stream()
+        _state["stream"] = _capi.private_stream("comm")
     return _state["stream"]
 
 

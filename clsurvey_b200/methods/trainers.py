@@ -17,6 +17,7 @@ import time
 
 import torch
 
+from .. import _capi
 from .. import dist as cdist
 from ..engine import LOSS_MEAN_CE, engine_of
 
@@ -36,8 +37,11 @@ class _CheckpointWriter:
     The reference pickles the whole module inline: ~0.15 s for VGG-11 with its reg_params (170 MB) -- as long as 50 training
     steps of this engine, on every validation improvement.  Here the caller takes a device-side snapshot (copy.deepcopy of the
     module: a few D2D copies, microseconds of stream time) and the thread does the D2H copies, pickling and file I/O while the
-    next steps run.  Semantics kept: a newer snapshot of the same file waits for the older one, and train_model does not return
-    before every file is on disk.  CLB_ASYNC_SAVE=0 restores inline saves."""
+    next steps run.  The thread works on its own CUDA stream: torch.save copies every storage device->host on the calling
+    thread's current stream, and on the default stream each of those ~50 copies would queue behind all the training steps the
+    main thread has already enqueued (measured: 1.28 s for four checkpoints instead of 0.49 s).  Semantics kept: a newer
+    snapshot of the same file waits for the older one, and train_model does not return before every file is on disk.
+    CLB_ASYNC_SAVE=0 restores inline saves."""
 
     def __init__(self):
         import collections
@@ -48,6 +52,7 @@ class _CheckpointWriter:
         self.busy = False
         self.thread = None
         self.error = None
+        self.stream = None
 
     def _worker(self):
         while True:
@@ -56,9 +61,18 @@ class _CheckpointWriter:
                     self.busy = False
                     self.lock.notify_all()
                     return
-                path, snap = self.pending.popitem(last=False)
+                path, (snap, ready) = self.pending.popitem(last=False)
             try:
+                t0 = time.time()
+                if self.stream is not None:
+                    with torch.cuda.stream(self.stream):
+                        self.stream.wait_event(ready)  # the snapshot's D2D copies, queued on the trainer's stream
+                        _to_host_inplace(snap)
+                t1 = time.time()
                 torch.save(snap, path)
+                if os.environ.get("CLB_SAVE_TRACE"):
+                    import sys
+                    sys.stderr.write("[ckpt] %s: to host %.3f s, torch.save %.3f s\n" % (os.path.basename(path), t1 - t0, time.time() - t1))
             except Exception as e:                    # surfaced by wait()
                 self.error = e
             del snap
@@ -70,8 +84,14 @@ class _CheckpointWriter:
             torch.save(obj, path)
             return
         snap = copy.deepcopy(obj)                     # device-side snapshot, ordered on the current stream
+        ready = None
+        if torch.cuda.is_available():
+            if self.stream is None:
+                self.stream = _capi.private_stream("checkpoint")
+            ready = torch.cuda.Event()
+            ready.record()
         with self.lock:
-            self.pending[path] = snap
+            self.pending[path] = (snap, ready)
             self.pending.move_to_end(path)
             if not self.busy:
                 self.busy = True
@@ -85,6 +105,35 @@ class _CheckpointWriter:
         if self.error is not None:
             e, self.error = self.error, None
             raise e
+
+
+def _to_host_inplace(obj, _seen=None):
+    """Move every CUDA tensor reachable from a checkpoint object (module / state_dict / optimizer state / reg_params, nested in
+    dicts, lists and tuples) to the host, keeping object identities: Parameters stay the keys of `reg_params`."""
+    seen = set() if _seen is None else _seen
+    if id(obj) in seen:
+        return
+    seen.add(id(obj))
+    if isinstance(obj, torch.Tensor):
+        if obj.is_cuda:
+            obj.data = obj.data.cpu()
+        if obj.grad is not None and obj.grad.is_cuda:
+            obj.grad.data = obj.grad.data.cpu()
+    elif isinstance(obj, torch.nn.Module):
+        for t in list(obj.parameters()) + list(obj.buffers()):
+            _to_host_inplace(t, seen)
+        for k, v in vars(obj).items():
+            if k not in ("_parameters", "_buffers", "_modules"):
+                _to_host_inplace(v, seen)
+        for m in obj.children():
+            _to_host_inplace(m, seen)
+    elif isinstance(obj, dict):
+        for k, v in obj.items():
+            _to_host_inplace(k, seen)
+            _to_host_inplace(v, seen)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            _to_host_inplace(v, seen)
 
 
 def set_lr(optimizer, lr, count, stop_ge=False):
@@ -118,7 +167,7 @@ class _StagedBatches:
 
     def __init__(self, loader, eng, squeeze, world, rk):
         self.it, self.eng, self.squeeze, self.world, self.rk = iter(loader), eng, squeeze, world, rk
-        self.side = torch.cuda.Stream() if eng.device.type == "cuda" else None
+        self.side = _capi.private_stream("h2d") if eng.device.type == "cuda" else None
         self.buf = [None, None]
         self.free_ev = [None, None]                  # recorded on the main stream when the step reading buffer k is launched
         self.k = 0

@@ -54,6 +54,10 @@ unsigned long long clb_launch_count(void); /* kernels launched by this library s
 /* stream-ordered zero fill (cudaMemsetAsync; a memset node under graph capture): the per-step resets of the loss /
  * #correct accumulators and of the gradient buffer -- optimizer.zero_grad() of train_EWC.py:177 */
 int clb_memset_zero(void* p, size_t bytes, void* stream);
+/* A new non-blocking stream of the current device, owned by the caller for the life of the process.  The host side wraps
+ * these for its side work (H2D staging of the next batch, checkpoint D2H, gradient all-reduce): torch.cuda.Stream() hands out
+ * pooled streams round-robin, which after 32 requests alias the stream a CUDA graph is being captured on. */
+int clb_stream_create(void** out);
 
 /* ------------------------------------------------------------------------------------------
  * Layer kernels (a2, a3).  Replace model(inputs) / loss.backward() of train_EWC.py:181-187.

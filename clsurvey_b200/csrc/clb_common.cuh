@@ -44,6 +44,29 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
         }                                                                          \
     } while (0)
 
+// Programmatic dependent launch.  Kernels of the per-step chain are launched with the programmatic-stream-serialization
+// attribute: a kernel may become resident while its predecessor in the stream is still draining (CTA by CTA for the persistent
+// GEMMs), runs its prologue, and blocks in pdl_wait() until the predecessor has completed and flushed its memory.  Every kernel
+// launched through launch_pdl() MUST call pdl_wait() before its first global-memory access; pdl_trigger() lets the successor in.
+// Captured into CUDA graphs as programmatic edges.  CLB_PDL=0 launches plainly.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+int pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled();
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -36,6 +36,11 @@ int mm_mode() {
     }
     return g_mm_mode;
 }
+int pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("CLB_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
 static unsigned long long g_launches = 0;
 void count_launch() { ++g_launches; }
 unsigned long long launches() { return g_launches; }

@@ -178,6 +178,8 @@ __global__ void __launch_bounds__(kLossThreads)
 softmax_loss_kernel(const float* __restrict__ logits, int ld, int col_off, int ncols, const int64_t* __restrict__ labels,
                     int B, int mode, float denom, float* __restrict__ loss_out, int* __restrict__ correct_out,
                     float* __restrict__ dlogits) {
+    pdl_trigger();
+    pdl_wait();
     float my_loss = 0.f;
     int my_corr = 0;
     for (int r = threadIdx.x; r < B; r += blockDim.x) {
@@ -315,8 +317,8 @@ int clb_softmax_loss(const float* logits, int ld, int col_off, int ncols, const 
     CLB_CHECK_ARG(mode == CLB_LOSS_MEAN_CE || mode == CLB_LOSS_SUM_NLL || mode == CLB_LOSS_SUM_SQ);
     CLB_CHECK_ARG(mode == CLB_LOSS_SUM_SQ || labels != nullptr);
     CLB_CHECK_ARG(mode != CLB_LOSS_MEAN_CE || mean_denominator > 0.f);
-    softmax_loss_kernel<<<1, kLossThreads, 0, as_stream(stream)>>>(logits, ld, col_off, ncols, labels, B, mode,
-                                                                    mean_denominator, loss_out, correct_out, dlogits); clb::count_launch();
+    launch_pdl(softmax_loss_kernel, dim3(1), dim3(kLossThreads), 0, as_stream(stream), logits, ld, col_off, ncols, labels, B, mode,
+               mean_denominator, loss_out, correct_out, dlogits); clb::count_launch();
     CLB_CHECK_LAUNCH();
     return CLB_OK;
 }

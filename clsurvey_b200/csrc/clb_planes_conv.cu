@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_planes_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                    const ConvArgs p) {
+    pdl_trigger();                                       // the next kernel of the chain may start its own prologue
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar = base + kStages * kStageBytes;
@@ -144,6 +145,8 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     tc_fence_after();
     const uint32_t tmem = *slot_ptr;
     const int cpb = p.Cred >> 6;                         // 64-channel blocks per tap
+    pdl_wait();                                          // barriers, TMEM and descriptors are set up: now wait for the producer of
+    //                                                      the operands (the predecessor kernel) to complete
 
     if (warp == 0) {
         // ================================================================================ TMA producer
@@ -384,7 +387,7 @@ static int launch(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtens
     static bool configured = false;
     if (!configured) { CLB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)); configured = true; }
     const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
-    kern<<<grid, kThreads, kSmemBytes, s>>>(a_hi, a_lo, b_hi, b_lo, p); clb::count_launch();
+    launch_pdl(kern, dim3(grid), dim3(kThreads), kSmemBytes, s, a_hi, a_lo, b_hi, b_lo, p); clb::count_launch();
     return CLB_OK;
 }
 

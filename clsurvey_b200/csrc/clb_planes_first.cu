@@ -35,6 +35,8 @@ __device__ __forceinline__ void wait_tile() { asm volatile("cp.async.wait_group 
 __global__ void __launch_bounds__(256, 2) conv1_pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ bias, uint16_t* __restrict__ y_hi,
                                                              uint16_t* __restrict__ y_lo, uint8_t* __restrict__ am, int N, int H, int W) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sm[];
     const int PH = H >> 1, PW = W >> 1, pitch = W + 4;
     float* w_s = sm;                                  // [27][64]
@@ -118,6 +120,8 @@ __global__ void __launch_bounds__(256) conv1_pool_bwd_kernel(const float* __rest
                                                              const uint16_t* __restrict__ dp_lo, const uint16_t* __restrict__ pooled_hi,
                                                              const uint8_t* __restrict__ am, float* __restrict__ part, int N, int H, int W,
                                                              int rows_per_cta) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sm[];
     const int PH = H >> 1, PW = W >> 1, pitch = W + 4;
     float* tiles = sm;                                // 2 x [3][4][pitch]
@@ -199,6 +203,8 @@ __global__ void __launch_bounds__(256) conv1_pool_bwd_kernel(const float* __rest
 // dw[k][27], db[k] = sum over CTAs (warp per output, lanes stride the CTAs in order, fixed shuffle tree)
 __global__ void __launch_bounds__(256) conv1_bwd_final_kernel(const float* __restrict__ part, float* __restrict__ dw, float* __restrict__ db,
                                                               int chunks) {
+    pdl_trigger();
+    pdl_wait();
     const int o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (o >= kF1K * 28) return;
     float s = 0.f;
@@ -219,7 +225,7 @@ int conv1_pool_fwd(const float* x, const float* w, const float* bias, uint16_t* 
     const size_t smem = (size_t)(kF1Taps * kF1K + 2 * 12 * (W + 4)) * 4;
     int grid = N * (H / 2);
     if (grid > sm_count() * 6) grid = sm_count() * 6;
-    conv1_pool_fwd_kernel<<<grid, 256, smem, s>>>(x, w, bias, y_hi, y_lo, am, N, H, W); clb::count_launch();
+    launch_pdl(conv1_pool_fwd_kernel, dim3(grid), dim3(256), smem, s, x, w, bias, y_hi, y_lo, am, N, H, W); clb::count_launch();
     return CLB_OK;
 }
 size_t conv1_bwd_ws_floats() { return (size_t)kF1Ctas * kF1K * 28; }
@@ -228,8 +234,8 @@ int conv1_pool_bwd(const float* x, const uint16_t* dp_hi, const uint16_t* dp_lo,
     const int rows = N * (H / 2);
     const int per = (rows + kF1Ctas - 1) / kF1Ctas, ctas = (rows + per - 1) / per;
     const size_t smem = (size_t)(2 * 12 * (W + 4) + kF1K * 28) * 4;
-    conv1_pool_bwd_kernel<<<ctas, 256, smem, s>>>(x, dp_hi, dp_lo, pooled_hi, am, part, N, H, W, per); clb::count_launch();
-    conv1_bwd_final_kernel<<<(kF1K * 28 + 7) / 8, 256, 0, s>>>(part, dw, db, ctas); clb::count_launch();
+    launch_pdl(conv1_pool_bwd_kernel, dim3(ctas), dim3(256), smem, s, x, dp_hi, dp_lo, pooled_hi, am, part, N, H, W, per); clb::count_launch();
+    launch_pdl(conv1_bwd_final_kernel, dim3((kF1K * 28 + 7) / 8), dim3(256), 0, s, part, dw, db, ctas); clb::count_launch();
     return CLB_OK;
 }
 

@@ -20,6 +20,8 @@ static inline int ew_grid(int64_t n, int threads) {
 __global__ void __launch_bounds__(256) weights_to_planes_kernel(const float* __restrict__ w, uint16_t* __restrict__ wf_hi,
                                                                 uint16_t* __restrict__ wf_lo, uint16_t* __restrict__ wt_hi,
                                                                 uint16_t* __restrict__ wt_lo, int K, int C, int taps) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t total = (int64_t)K * C, gs = (int64_t)gridDim.x * blockDim.x;
     const bool dgrad = blockIdx.y == 1;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gs) {
@@ -43,7 +45,7 @@ __global__ void __launch_bounds__(256) weights_to_planes_kernel(const float* __r
 int weights_to_planes(const float* w, uint16_t* wf_hi, uint16_t* wf_lo, uint16_t* wt_hi, uint16_t* wt_lo, int K, int C, int taps,
                       cudaStream_t s) {
     dim3 grid(ew_grid((int64_t)K * C, 256), wt_hi ? 2 : 1);
-    weights_to_planes_kernel<<<grid, 256, 0, s>>>(w, wf_hi, wf_lo, wt_hi, wt_lo, K, C, taps); clb::count_launch();
+    launch_pdl(weights_to_planes_kernel, dim3(grid), dim3(256), 0, s, w, wf_hi, wf_lo, wt_hi, wt_lo, K, C, taps); clb::count_launch();
     return CLB_OK;
 }
 
@@ -57,6 +59,8 @@ struct WeightBatch {
     int K[kMax], C[kMax], taps[kMax];                // taps = 9 (3x3 conv weight [K][C][3][3]) or 1 (nn.Linear weight [K][C])
 };
 __global__ void __launch_bounds__(256) weights_to_planes_batch_kernel(const __grid_constant__ WeightBatch b) {
+    pdl_trigger();
+    pdl_wait();
     // thread = two adjacent elements of the contiguous output dimension (c for the forward layout, k for the dgrad layout):
     // 4-byte stores, coalesced along that dimension; C and K are multiples of 64
     const int layer = blockIdx.y >> 1;
@@ -98,7 +102,7 @@ int weights_to_planes_batch(int n, const float* const* w, void* const* wf_hi, vo
     }
     int gx = (int)((mx / 2 + 255) / 256);
     if (gx > 256) gx = 256;
-    weights_to_planes_batch_kernel<<<dim3(gx, 2 * n), 256, 0, s>>>(b); clb::count_launch();
+    launch_pdl(weights_to_planes_batch_kernel, dim3(gx, 2 * n), dim3(256), 0, s, b); clb::count_launch();
     return CLB_OK;
 }
 
@@ -114,6 +118,8 @@ __global__ void __launch_bounds__(256) pool_planes_fwd_kernel(const uint16_t* __
                                                               uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo,
                                                               float* __restrict__ y_f32, uint8_t* __restrict__ am, int N, int H,
                                                               int W, int C) {
+    pdl_trigger();
+    pdl_wait();
     const int PH = H >> 1, PW = W >> 1, C8 = C >> 3;
     const int64_t total = (int64_t)N * PH * PW * C8, gs = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gs) {
@@ -161,6 +167,8 @@ __global__ void __launch_bounds__(256) pool_planes_fwd_kernel(const uint16_t* __
 __global__ void __launch_bounds__(256) pool_nchw_to_planes_kernel(const float* __restrict__ x, uint16_t* __restrict__ y_hi,
                                                                   uint16_t* __restrict__ y_lo, uint8_t* __restrict__ am, int N,
                                                                   int C, int H, int W) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sm[];                                   // [PW][65] values, then [PW][65] arg-max as float bits
     const int PH = H >> 1, PW = W >> 1;
     const int cb = blockIdx.y * 64, ph = blockIdx.x % PH, n = blockIdx.x / PH;
@@ -198,6 +206,8 @@ __global__ void __launch_bounds__(256) pool_planes_bwd_kernel(const uint16_t* __
                                                               const float* __restrict__ pooled_f32, const uint8_t* __restrict__ am,
                                                               uint16_t* __restrict__ dx_hi, uint16_t* __restrict__ dx_lo, int N, int H,
                                                               int W, int C) {
+    pdl_trigger();
+    pdl_wait();
     const int PH = H >> 1, PW = W >> 1, C8 = C >> 3;
     const int64_t total = (int64_t)N * PH * PW * C8, gs = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gs) {
@@ -254,6 +264,8 @@ __global__ void __launch_bounds__(256) pool_planes_bwd_kernel(const uint16_t* __
 __global__ void __launch_bounds__(256) pool_planes_bwd_to_nchw_kernel(const uint16_t* __restrict__ dy_hi, const uint16_t* __restrict__ dy_lo,
                                                                       const uint16_t* __restrict__ pooled_hi, const uint8_t* __restrict__ am,
                                                                       float* __restrict__ dx, int N, int C, int H, int W) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sm[];                                   // [64][2][W + 1]
     const int PH = H >> 1, PW = W >> 1, ldw = W + 1;
     const int cb = blockIdx.y * 64, ph = blockIdx.x % PH, n = blockIdx.x / PH;
@@ -276,23 +288,23 @@ __global__ void __launch_bounds__(256) pool_planes_bwd_to_nchw_kernel(const uint
 int pool_fwd(const uint16_t* x_hi, const uint16_t* x_lo, uint16_t* y_hi, uint16_t* y_lo, float* y_f32, uint8_t* am, int N, int H,
              int W, int C, int flat, cudaStream_t s) {
     const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
-    if (y_f32) pool_planes_fwd_kernel<1><<<ew_grid(total, 256), 256, 0, s>>>(x_hi, x_lo, nullptr, nullptr, y_f32, am, N, H, W, C);
-    else if (flat) pool_planes_fwd_kernel<2><<<ew_grid(total, 256), 256, 0, s>>>(x_hi, x_lo, y_hi, y_lo, nullptr, am, N, H, W, C);
-    else pool_planes_fwd_kernel<0><<<ew_grid(total, 256), 256, 0, s>>>(x_hi, x_lo, y_hi, y_lo, nullptr, am, N, H, W, C);
+    if (y_f32) launch_pdl(pool_planes_fwd_kernel<1>, dim3(ew_grid(total, 256)), dim3(256), 0, s, x_hi, x_lo, nullptr, nullptr, y_f32, am, N, H, W, C);
+    else if (flat) launch_pdl(pool_planes_fwd_kernel<2>, dim3(ew_grid(total, 256)), dim3(256), 0, s, x_hi, x_lo, y_hi, y_lo, nullptr, am, N, H, W, C);
+    else launch_pdl(pool_planes_fwd_kernel<0>, dim3(ew_grid(total, 256)), dim3(256), 0, s, x_hi, x_lo, y_hi, y_lo, nullptr, am, N, H, W, C);
     clb::count_launch();
     return CLB_OK;
 }
 int pool_fwd_from_nchw(const float* x, uint16_t* y_hi, uint16_t* y_lo, uint8_t* am, int N, int C, int H, int W, cudaStream_t s) {
     const size_t smem = (size_t)(W / 2) * 65 * 8;
-    pool_nchw_to_planes_kernel<<<dim3(N * (H / 2), C / 64), 256, smem, s>>>(x, y_hi, y_lo, am, N, C, H, W); clb::count_launch();
+    launch_pdl(pool_nchw_to_planes_kernel, dim3(N * (H / 2), C / 64), dim3(256), smem, s, x, y_hi, y_lo, am, N, C, H, W); clb::count_launch();
     return CLB_OK;
 }
 int pool_bwd(const uint16_t* dy_hi, const uint16_t* dy_lo, const float* dy_f32, const uint16_t* pooled_hi, const float* pooled_f32,
              const uint8_t* am, uint16_t* dx_hi, uint16_t* dx_lo, int N, int H, int W, int C, int flat, cudaStream_t s) {
     const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
-    if (dy_f32) pool_planes_bwd_kernel<1><<<ew_grid(total, 256), 256, 0, s>>>(nullptr, nullptr, dy_f32, nullptr, pooled_f32, am, dx_hi, dx_lo, N, H, W, C);
-    else if (flat) pool_planes_bwd_kernel<2><<<ew_grid(total, 256), 256, 0, s>>>(dy_hi, dy_lo, nullptr, pooled_hi, nullptr, am, dx_hi, dx_lo, N, H, W, C);
-    else pool_planes_bwd_kernel<0><<<ew_grid(total, 256), 256, 0, s>>>(dy_hi, dy_lo, nullptr, pooled_hi, nullptr, am, dx_hi, dx_lo, N, H, W, C);
+    if (dy_f32) launch_pdl(pool_planes_bwd_kernel<1>, dim3(ew_grid(total, 256)), dim3(256), 0, s, nullptr, nullptr, dy_f32, nullptr, pooled_f32, am, dx_hi, dx_lo, N, H, W, C);
+    else if (flat) launch_pdl(pool_planes_bwd_kernel<2>, dim3(ew_grid(total, 256)), dim3(256), 0, s, dy_hi, dy_lo, nullptr, pooled_hi, nullptr, am, dx_hi, dx_lo, N, H, W, C);
+    else launch_pdl(pool_planes_bwd_kernel<0>, dim3(ew_grid(total, 256)), dim3(256), 0, s, dy_hi, dy_lo, nullptr, pooled_hi, nullptr, am, dx_hi, dx_lo, N, H, W, C);
     clb::count_launch();
     return CLB_OK;
 }
@@ -300,6 +312,8 @@ int pool_bwd(const uint16_t* dy_hi, const uint16_t* dy_lo, const float* dy_f32, 
 // ------------------------------------------------------------------------------------------------ fp32 <-> planes
 __global__ void __launch_bounds__(256) planes_to_f32_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo,
                                                             float* __restrict__ out, int64_t n) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t gs = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) out[i] = join1(hi[i], lo[i]);
 }
@@ -307,6 +321,8 @@ __global__ void __launch_bounds__(256) planes_to_f32_kernel(const uint16_t* __re
 // planes nn.Linear applied to the fp32 gradient that arrives from a layer outside the planes pipeline
 __global__ void __launch_bounds__(256) f32_to_planes_kernel(const float* __restrict__ x, const uint16_t* __restrict__ mask_hi,
                                                             uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t n) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t gs = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gs) {
         float v = x[i];
@@ -317,17 +333,17 @@ __global__ void __launch_bounds__(256) f32_to_planes_kernel(const float* __restr
     }
 }
 int planes_to_f32(const uint16_t* hi, const uint16_t* lo, float* out, int64_t n, cudaStream_t s) {
-    planes_to_f32_kernel<<<ew_grid(n, 256), 256, 0, s>>>(hi, lo, out, n); clb::count_launch();
+    launch_pdl(planes_to_f32_kernel, dim3(ew_grid(n, 256)), dim3(256), 0, s, hi, lo, out, n); clb::count_launch();
     return CLB_OK;
 }
 int f32_to_planes(const float* x, const uint16_t* mask_hi, uint16_t* hi, uint16_t* lo, int64_t n, cudaStream_t s) {
-    f32_to_planes_kernel<<<ew_grid(n, 256), 256, 0, s>>>(x, mask_hi, hi, lo, n); clb::count_launch();
+    launch_pdl(f32_to_planes_kernel, dim3(ew_grid(n, 256)), dim3(256), 0, s, x, mask_hi, hi, lo, n); clb::count_launch();
     return CLB_OK;
 }
 int pool_bwd_to_nchw(const uint16_t* dy_hi, const uint16_t* dy_lo, const uint16_t* pooled_hi, const uint8_t* am, float* dx, int N,
                      int C, int H, int W, cudaStream_t s) {
     const size_t smem = (size_t)64 * 2 * (W + 1) * 4;
-    pool_planes_bwd_to_nchw_kernel<<<dim3(N * (H / 2), C / 64), 256, smem, s>>>(dy_hi, dy_lo, pooled_hi, am, dx, N, C, H, W); clb::count_launch();
+    launch_pdl(pool_planes_bwd_to_nchw_kernel, dim3(N * (H / 2), C / 64), dim3(256), smem, s, dy_hi, dy_lo, pooled_hi, am, dx, N, C, H, W); clb::count_launch();
     return CLB_OK;
 }
 
@@ -337,6 +353,8 @@ int pool_bwd_to_nchw(const uint16_t* dy_hi, const uint16_t* dy_lo, const uint16_
 constexpr int kBiasChunks = 592;
 __global__ void __launch_bounds__(256, 6) bias_partials_kernel(const uint16_t* __restrict__ dy_hi, const uint16_t* __restrict__ dy_lo,
                                                             float* __restrict__ part, int64_t npix, int K, int64_t pix_per_chunk) {
+    pdl_trigger();
+    pdl_wait();
     // thread = 8 channels (one 16-byte load per plane) of every `rows`-th pixel of the chunk; channel groups beyond the CTA's
     // 256 threads are handled in further passes
     const int K8 = K >> 3;
@@ -379,6 +397,8 @@ __global__ void __launch_bounds__(256, 6) bias_partials_kernel(const uint16_t* _
 }
 // one warp per channel: lane l adds chunks l, l + 32, ... in order, then a fixed xor-shuffle tree (deterministic)
 __global__ void __launch_bounds__(256) bias_final_kernel(const float* __restrict__ part, float* __restrict__ db, int K, int chunks) {
+    pdl_trigger();
+    pdl_wait();
     const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (k >= K) return;
     float s = 0.f;
@@ -390,8 +410,8 @@ size_t bias_ws_floats(int K) { return (size_t)kBiasChunks * K; }
 int bias_grad(const uint16_t* dy_hi, const uint16_t* dy_lo, float* db, float* part, int64_t npix, int K, cudaStream_t s) {
     const int64_t per = (npix + kBiasChunks - 1) / kBiasChunks;
     const int chunks = (int)((npix + per - 1) / per);
-    bias_partials_kernel<<<chunks, 256, 0, s>>>(dy_hi, dy_lo, part, npix, K, per); clb::count_launch();
-    bias_final_kernel<<<(K + 7) / 8, 256, 0, s>>>(part, db, K, chunks); clb::count_launch();
+    launch_pdl(bias_partials_kernel, dim3(chunks), dim3(256), 0, s, dy_hi, dy_lo, part, npix, K, per); clb::count_launch();
+    launch_pdl(bias_final_kernel, dim3((K + 7) / 8), dim3(256), 0, s, part, db, K, chunks); clb::count_launch();
     return CLB_OK;
 }
 
@@ -403,6 +423,8 @@ int bias_grad(const uint16_t* dy_hi, const uint16_t* dy_lo, float* db, float* pa
 template <int TAPS>
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, float* __restrict__ omega,
                                                            int K, int C, int splits, int imp_mode, float imp_a, float imp_b) {
+    pdl_trigger();
+    pdl_wait();
     // warp = 32 consecutive channels of one filter k: reads are coalesced along c (ws is [z][k][tap][c]), the 288 results are
     // transposed through shared memory and written as one contiguous run of dw[k][c0..c0+31][9]
     __shared__ float buf[8][32 * TAPS];
@@ -440,8 +462,8 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 }
 int wgrad_reduce(const float* ws, float* dw, float* omega, int K, int C, int taps, int splits, int imp_mode, float imp_a, float imp_b,
                  cudaStream_t s) {
-    if (taps == 9) wgrad_reduce_kernel<9><<<ew_grid((int64_t)K * C, 32), 256, 0, s>>>(ws, dw, omega, K, C, splits, imp_mode, imp_a, imp_b);
-    else wgrad_reduce_kernel<1><<<ew_grid((int64_t)K * C, 32), 256, 0, s>>>(ws, dw, omega, K, C, splits, imp_mode, imp_a, imp_b);
+    if (taps == 9) launch_pdl(wgrad_reduce_kernel<9>, dim3(ew_grid((int64_t)K * C, 32)), dim3(256), 0, s, ws, dw, omega, K, C, splits, imp_mode, imp_a, imp_b);
+    else launch_pdl(wgrad_reduce_kernel<1>, dim3(ew_grid((int64_t)K * C, 32)), dim3(256), 0, s, ws, dw, omega, K, C, splits, imp_mode, imp_a, imp_b);
     clb::count_launch();
     return CLB_OK;
 }

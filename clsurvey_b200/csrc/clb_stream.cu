@@ -50,6 +50,8 @@ __device__ __forceinline__ void sgd_elem(float& th, float g, float om, float ts,
 __global__ void __launch_bounds__(kThreads)
 sgd_penalty_kernel(float* __restrict__ theta, const float* __restrict__ g, const float* __restrict__ omega,
                    const float* __restrict__ tstar, float* __restrict__ buf, int64_t n, int64_t n_pen, SgdArgs a) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t n4 = n >> 2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -246,8 +248,8 @@ int clb_sgd_penalty_step(float* theta, const float* g, const float* omega, const
     CLB_CHECK_ARG(aligned16(theta) && aligned16(g) && aligned16(buf) && aligned16(omega) && aligned16(theta_star));
     if (n == 0) return CLB_OK;
     SgdArgs a{two_lambda, lr, momentum, weight_decay, grad_scale, first_step ? 1 : 0};
-    sgd_penalty_kernel<<<stream_grid(n >> 2), kThreads, 0, as_stream(stream)>>>(theta, g, omega, theta_star, buf, n,
-                                                                                 n_penalised, a); clb::count_launch();
+    launch_pdl(sgd_penalty_kernel, dim3(stream_grid(n >> 2)), dim3(kThreads), 0, as_stream(stream), theta, g, omega, theta_star, buf, n,
+               n_penalised, a); clb::count_launch();
     CLB_CHECK_LAUNCH();
     return CLB_OK;
 }

@@ -111,15 +111,15 @@ def _comm_stream():
     return _state["stream"]
 
 
-def start_tail_allreduce(engine, cut):
-    """Called by Engine.backward once every gradient at flat offset >= cut is final: all-reduce grad[cut:] on the
-    communication stream while the compute stream goes on with the backward pass of the first layers.  Both
-    collectives of a step are issued on the communication stream, in the same order on every rank."""
+def start_tail_allreduce(engine, cut, end=None):
+    """Called by Engine.backward once every gradient at flat offset >= cut is final: all-reduce grad[cut:end] (one bucket of
+    Engine._dp_buckets) on the communication stream while the compute stream goes on with the backward pass of the layers
+    in front.  All collectives of a step are issued on the communication stream, in the same order on every rank."""
     main, side = torch.cuda.current_stream(), _comm_stream()
     ev = torch.cuda.Event()
     ev.record(main)
     side.wait_event(ev)
-    tail = engine.grad[cut:]
+    tail = engine.grad[cut:end]
     _capi.call("clb_nccl_allreduce_f32", _state["comm"], tail.data_ptr(), tail.numel(), side.cuda_stream)
     engine.n_launch += 1
     return cut

@@ -150,6 +150,7 @@ class Engine:
         self._sig = sig
         self._graphs = {}
         self._dp_cut_cache = None                     # offsets may have moved (head swap)
+        self._dp_buckets_cache = None
         self._compile()
 
     def view(self, flat, i):
@@ -525,6 +526,27 @@ class Engine:
             self._dp_cut_cache = cut
         return self._dp_cut_cache
 
+    def _dp_buckets(self):
+        """The tail behind _dp_cut() in up to three buckets, [(op index, flat offset, end offset)] in the order backward()
+        completes them (back to front): a bucket is closed at a layer boundary once it holds >= 20 % of the parameters.
+        Each bucket's all-reduce starts as soon as its first layer's gradient is final (VGG-11: [conv8, fc1, fc2, head],
+        [conv7], [conv5, conv6] -- 14.7 / 9.4 / 14.2 MB -- then the head conv1-4, 3.8 MB, after the last layer)."""
+        if getattr(self, "_dp_buckets_cache", None) is None:
+            cut_op, cut_off = self._dp_cut()
+            buckets = []
+            if cut_off:
+                end, acc = self.total, 0
+                layers = [(i, self.offsets[op["w"]]) for i, op in enumerate(self.ops) if op["kind"] in ("conv", "linear")]
+                for i, o in reversed(layers):
+                    if o < cut_off:
+                        break
+                    acc = end - o
+                    if (o == cut_off) or (acc >= 0.2 * self.total and o % 4 == 0 and len(buckets) < 2):
+                        buckets.append((i, o, end))
+                        end = o
+            self._dp_buckets_cache = buckets
+        return self._dp_buckets_cache
+
     def backward(self, accumulate=False, dp_overlap=False, importance=None):
         """dlogits -> parameter gradients (flat self.grad).  importance = (1, data_len) [EWC: omega += g*g/data_len,
         main_EWC.py:151-156] or (2, prev_size, curr_size) [MAS: omega = (omega*prev + |g|)/curr, train_MAS.py:163-177]
@@ -540,11 +562,11 @@ class Engine:
             assert not accumulate and self.omega is not None
             imp_mode, imp_a = int(importance[0]), float(importance[1])
             imp_b = float(importance[2]) if len(importance) > 2 else 0.0
-        cut_op, cut_off = (0, 0)
+        buckets = []
         if dp_overlap and not accumulate:
             from . import dist as _dist
             if _dist.is_distributed() and self.grad.is_cuda:
-                cut_op, cut_off = self._dp_cut()
+                buckets = list(self._dp_buckets())
         gdst = self.grad
         if accumulate:
             if self._grad_alt is None:
@@ -556,9 +578,10 @@ class Engine:
         for i in range(len(self.ops) - 1, -1, -1):
             op = self.ops[i]
             k = op["kind"]
-            if cut_off and i == cut_op - 1:
+            while buckets and i == buckets[0][0] - 1:                 # every gradient at offset >= buckets[0][1] is final
                 from . import dist as _dist
-                self._dp_pending = _dist.start_tail_allreduce(self, cut_off)
+                _, b_off, b_end = buckets.pop(0)
+                self._dp_pending = _dist.start_tail_allreduce(self, b_off, b_end)
             if k == "linear" and op.get("planes"):
                 x_pl = op["inp"]                                      # planes of this layer's input
                 if not isinstance(d, (list, tuple)) and d.dim() == 1:  # fp32 gradient from the head: ReLU backward + planes
@@ -702,9 +725,8 @@ class Engine:
         if dp_overlap:
             from . import dist as _dist
             if _dist.is_distributed() and self.grad.is_cuda:
-                _, cut_off = self._dp_cut()
-                if cut_off:
-                    self._dp_pending = _dist.start_tail_allreduce(self, cut_off)
+                for _, b_off, b_end in self._dp_buckets():
+                    self._dp_pending = _dist.start_tail_allreduce(self, b_off, b_end)
 
     # ------------------------------------------------------------------ composite steps
     def fwd_loss_bwd(self, x, y, mode=LOSS_MEAN_CE, denom=None, train=True, masks=None, col_off=0, ncols=None,

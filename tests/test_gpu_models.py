@@ -211,6 +211,16 @@ def test_dp_gradient_cut_points():
             assert all(eng.offsets[op["w"]] >= off for op in eng.ops[i:] if op["kind"] in ("conv", "linear"))
         if name == "VGG11":                      # conv1-4 = 1728+64 + 73728+128 + 294912+256 + 589824+256
             assert off == 960896 and eng.ops[i]["C"] == 256 and eng.ops[i]["K"] == 512
+        # the tail in buckets (Engine._dp_buckets): back to front, contiguous, each starting at a layer, covering [off, total)
+        b = eng._dp_buckets()
+        assert (len(b) == 0) == (off == 0) and len(b) <= 3
+        end = eng.total
+        for bi, bo, be in b:
+            assert be == end and bo < be and bo % 4 == 0 and eng.offsets[eng.ops[bi]["w"]] == bo
+            end = bo
+        assert not b or end == off
+        if name == "VGG11":                      # [conv8, fc1, fc2, head], [conv7], [conv5, conv6]
+            assert [x[1] for x in b] == [6860672, 4500864, 960896]
 
 
 def test_gem_observe_alexnet_c5_scale():

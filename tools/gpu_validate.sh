@@ -8,7 +8,7 @@ timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; 
 timeout 300 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-graph --no-cpu-baseline > /dev/null 2>&1; echo "ncu launch list rc=$?"
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_planes_kernel -c 45 -f -o gpurun_out/prof_conv \
+timeout 400 ncu --set full --clock-control none -k regex:conv_planes_kernel -c 27 -f -o gpurun_out/prof_conv \
     python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline > /dev/null 2>&1; echo "ncu full rc=$?"
 # read here with: ncu -i gpurun_out/prof_conv.ncu-rep --page raw --csv > profiles/rN_ncu_full_conv.csv
 #                 python tools/ncu_traffic.py profiles/rN_ncu_full_conv.csv > profiles/rN_conv_traffic.json

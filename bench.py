@@ -305,6 +305,25 @@ def run_gpu_arm(args):
         sampler.start()
     ms = timed(step_dev, args.steps)
     value = GLOBAL_BATCH * args.steps / (ms / 1e3)
+    # N > 1: the same per-rank step without its collectives (every rank steps on its local gradient; train_model re-syncs the
+    # replicas before the end-to-end region) -> compute time and exposed all-reduce time of the data-parallel step
+    comp_ms = None
+    if world > 1 and state["run"] is not None:
+        import torch.distributed as td
+        ok = 1
+        try:
+            with cdist.local_only():
+                run_local = eng.graphed(("bench_local", per), per, body)
+                for i in range(2):
+                    run_local(xs_d[i % NB], ys_d[i % NB])
+            torch.cuda.synchronize()
+        except Exception as e:
+            sys.stderr.write("local-only step graph failed: %r\n" % (e,))
+            ok = 0
+        flag = torch.tensor([ok], device=dev)
+        td.all_reduce(flag, op=td.ReduceOp.MIN)
+        if int(flag.item()):
+            comp_ms = timed(lambda i: run_local(xs_d[i % NB], ys_d[i % NB]), args.steps) / args.steps
     mode_name = {0: "fp32 FFMA (SIMT)", 1: "tf32x3 tcgen05", 2: "tf32x1 tcgen05",
                  3: "bf16x3 tcgen05: TMA-fed NHWC hi/lo planes (conv + hidden Linear layers) + tf32x3 (task head)"}[args.mm_mode]
     # per-kernel timing of the dominant (conv) launches: the same K steps run eagerly with CUDA events around every conv
@@ -437,6 +456,10 @@ def run_gpu_arm(args):
             "gpu_launches": int(launches),
             "roofline": roof, "roofline_n64": roof64, "roofline_fisher": fisher, "cpu_baseline": cpu,
         }
+        if comp_ms is not None:                              # data-parallel step = per-rank compute + exposed all-reduce
+            line["details"]["compute_ms_per_step"] = comp_ms
+            line["details"]["exposed_allreduce_ms_per_step"] = max(ms / args.steps - comp_ms, 0.0)
+            line["details"]["conv_ms_per_step_timed_call_by_call"] = roof.get("ms_per_step_in_kernel") if roof else None
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     # NCCL keeps a communicator alive while a captured graph still references it: drop the graphs first, and never let
     # a slow teardown hold the job after the result line is out

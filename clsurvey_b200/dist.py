@@ -32,6 +32,20 @@ def is_distributed():
     return _state["world"] > 1
 
 
+class local_only:
+    """Context manager: inside it this rank behaves like a single-GPU job (no collectives are issued).  bench.py uses it to
+    time a rank's step WITHOUT its all-reduces, which gives the exposed communication time of the data-parallel step."""
+
+    def __enter__(self):
+        self._saved = _state["world"]
+        _state["world"] = 1
+        return self
+
+    def __exit__(self, *exc):
+        _state["world"] = self._saved
+        return False
+
+
 def init(backend=None):
     """Initialise from torchrun's env (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*).  No-op for a single process."""
     import torch.distributed as td

@@ -357,11 +357,6 @@ conv_planes_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-static int mn_swap() {                                  // bring-up switch (tools/planes_check.py): CLB_PLANES_MN_SWAP=1 swaps LBO / SBO
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("CLB_PLANES_MN_SWAP"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v;
-}
 static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 // nn.Linear(in, out) on the same kernel: a 1x1 "conv" over a 1x1 map whose 128-row tiles are 128 samples
@@ -450,7 +445,7 @@ int conv_wgrad_partials(const uint16_t* x_hi, const uint16_t* x_lo, const uint16
     p.n_tiles_n = (p.ncb + 1) / 2;
     p.n_items = p.n_tiles_m * p.n_tiles_n * p.splits;
     p.ws = ws;
-    p.mn_lbo = mn_swap() ? 1024u : 8192u; p.mn_sbo = mn_swap() ? 8192u : 1024u;
+    p.mn_lbo = 8192u; p.mn_sbo = 1024u;              // MN-major, 128B swizzle: 64-wide MN atoms 8 KB apart, 8-row K groups 1 KB apart
     *splits_out = p.splits;
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     int rc;
